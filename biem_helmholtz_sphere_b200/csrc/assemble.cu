@@ -1,0 +1,381 @@
+// K3 (right-hand side) and K4 (system assembly).
+//
+// A[(b,h),(b',h')] = SD_{n'}(rho_b') * ( b==b' ? delta_{hh'} (alpha_b h_n + beta_b k h_n')(k rho_b)
+//                                                : (S|R)_{h',h}(c_b - c_b') (alpha_b j_n + beta_b k j_n')(k rho_b) )
+// (S|R)_{h',h}(t) = sum_terms coef(h,h',t) * i^{n+n''-n'} h_{n''}(k|t|) Y_{h''}(t^)           
+//
+// The real coupling coefficients `coef` (Gaunt-type triple integrals, k-independent) live in the plan as
+// 8x64 tiles in ELL form.  A CTA owns one tile: it stages the tile's coefficient/index layers in shared
+// memory ONCE with 1-D TMA bulk copies and then loops over ball pairs, for each pair building the
+// translation vector S_{h''}(t) = i^{n''} h_{n''}(k|t|) Y_{h''}(t^) in shared memory and contracting it
+// against the resident tile (2 DFMA per term).  Output rows are written as 1 KB contiguous segments.
+// The i^{n}, (-i)^{n'} phase split and the radial row/column factors are folded into two small vectors.
+#include "harmonics.cuh"
+#include "radial.cuh"
+#include "special.cuh"
+
+#define ASM_THREADS 256
+#define ASM_LAYER_COEF (BHS_TILE_E * 8)
+#define ASM_LAYER_IDX (BHS_TILE_E * 2)
+
+// ---- pre-kernels --------------------------------------------------------------------------------------
+// translation vectors t = c_b - c_b' for every ordered pair (b, b'):  tv[i][b*B+b'], dist[b*B+b']
+__global__ void pair_vectors_kernel(int d, int B, const double* __restrict__ centers, double* __restrict__ tv,
+                                    double* __restrict__ dist) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t np = (int64_t)B * B;
+    if (i >= np) return;
+    int b = (int)(i / B), bp = (int)(i % B);
+    double r2 = 0.0;
+    for (int a = 0; a < d; ++a) {
+        double t = centers[(int64_t)b * d + a] - centers[(int64_t)bp * d + a];
+        if (b == bp) t = (a == 0) ? 1.0 : 0.0;  // dummy direction for the unused diagonal pair
+        tv[(int64_t)a * np + i] = t;
+        r2 += t * t;
+    }
+    dist[i] = sqrt(r2);
+}
+
+struct SmArrA {
+    double* p;
+    int stride;
+    __device__ __forceinline__ double& operator[](int n) const { return p[(size_t)n * stride]; }
+};
+// hp[s][pair][n''] = i^{n''} h_{n''}(k_s |t_pair|), n'' < L2
+__global__ void pair_radial_kernel(int d, int L2, int n_store, int B, int nsys, const double* __restrict__ ks,
+                                   const double* __restrict__ dist, cplx* __restrict__ hp) {
+    extern __shared__ __align__(16) double sm[];
+    const int T = blockDim.x;
+    SmArrA hr{sm + threadIdx.x, T};
+    SmArrA hi{sm + (size_t)n_store * T + threadIdx.x, T};
+    int64_t np = (int64_t)B * B, total = np * nsys;
+    for (int64_t i = (int64_t)blockIdx.x * T + threadIdx.x; i < total; i += (int64_t)gridDim.x * T) {
+        int s = (int)(i / np);
+        int64_t pr = i % np;
+        if (pr / B == pr % B) {
+            for (int n = 0; n < L2; ++n) hp[i * L2 + n] = cmake(0.0, 0.0);
+            continue;
+        }
+        hankel_upward(d, ks[s] * dist[pr], L2 - 1, hr, hi);
+        for (int n = 0; n < L2; ++n) hp[i * L2 + n] = cmul_ipow(cmake(hr[n], hi[n]), n);
+    }
+}
+
+// per-system row / column / diagonal factors:
+//   rowf[s][b][h] = i^n (alpha_b j_n + beta_b k j_n')      colf[s][b][h] = (-i)^n SD_n(rho_b)
+//   diag[s][b][h] = SD_n (alpha_b h_n + beta_b k h_n')
+__global__ void factors_kernel(int d, int L, int H, int B, int nsys, const double* __restrict__ radii,
+                               const double* __restrict__ ks, const double* __restrict__ etas,
+                               const cplx* __restrict__ alpha, const cplx* __restrict__ beta,
+                               const double4* __restrict__ rad, const int32_t* __restrict__ deg,
+                               cplx* __restrict__ rowf, cplx* __restrict__ colf, cplx* __restrict__ diag) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t total = (int64_t)nsys * B * H;
+    if (i >= total) return;
+    int h = (int)(i % H);
+    int b = (int)((i / H) % B);
+    int s = (int)(i / ((int64_t)H * B));
+    int n = deg[h];
+    double k = ks[s], eta = etas ? etas[s] : 1.0;
+    double4 r = rad[((int64_t)s * B + b) * L + n];
+    cplx al = alpha ? alpha[b] : cmake(1.0, 0.0);
+    cplx be = beta ? beta[b] : cmake(0.0, 0.0);
+    cplx bek = cscale(be, k);
+    cplx reg = cadd(cscale(al, r.x), cscale(bek, r.y));
+    cplx sing = cadd(cmul(al, cmake(r.x, r.z)), cmul(bek, cmake(r.y, r.w)));
+    cplx sd = sd_coef(d, k, eta, radii[b], r.x, r.y);
+    if (rowf) rowf[i] = cmul_ipow(reg, n);
+    if (colf) colf[i] = cmul_ipow(sd, -n);
+    if (diag) diag[i] = cmul(sd, sing);
+}
+
+// ---- the assembly kernel --------------------------------------------------------------------------------
+struct AsmArgs {
+    int B, H, H2, L2, nt_res, pairs_per_cta;
+    const bhs_tile_hdr* tiles;
+    const double* coef;
+    const uint16_t* cidx;
+    const int32_t* deg2;
+    const cplx* Y2;    // [B*B][H2]
+    const cplx* hp;    // [nsys][B*B][L2]
+    const cplx* rowf;  // [nsys][B][H]
+    const cplx* colf;
+    const cplx* diag;
+    cplx* A;
+    int64_t ld, sys_stride;
+};
+
+__global__ void __launch_bounds__(ASM_THREADS) assemble_kernel(AsmArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    const int tid = threadIdx.x;
+    const bhs_tile_hdr hd = a.tiles[blockIdx.x];
+    const int tiles_c = (a.H + BHS_TILE_C - 1) / BHS_TILE_C;
+    const int tr = blockIdx.x / tiles_c, tc = blockIdx.x % tiles_c;
+    const int sys = blockIdx.z;
+    const int nt = hd.nt, nt_res = a.nt_res;
+    double* s_coef = reinterpret_cast<double*>(smem_raw);
+    uint16_t* s_idx = reinterpret_cast<uint16_t*>(smem_raw + (size_t)nt_res * ASM_LAYER_COEF);
+    cplx* s_sy = reinterpret_cast<cplx*>(smem_raw + (size_t)nt_res * (ASM_LAYER_COEF + ASM_LAYER_IDX));
+    const bool resident = nt <= nt_res;
+    uint32_t phase = 0;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (resident && nt > 0) {
+        if (tid == 0) {
+            mbar_expect_tx(&bar, (uint32_t)(nt * (ASM_LAYER_COEF + ASM_LAYER_IDX)));
+            tma_load_1d(s_coef, a.coef + hd.coef_off, (uint32_t)(nt * ASM_LAYER_COEF), &bar);
+            tma_load_1d(s_idx, a.cidx + hd.idx_off, (uint32_t)(nt * ASM_LAYER_IDX), &bar);
+        }
+        mbar_wait(&bar, phase);
+        phase ^= 1;
+    }
+    // this thread's two entries
+    const int e0 = tid, e1 = tid + ASM_THREADS;
+    const int r0 = e0 / BHS_TILE_C, c0 = e0 % BHS_TILE_C, r1 = e1 / BHS_TILE_C, c1 = e1 % BHS_TILE_C;
+    const int h0 = tr * BHS_TILE_R + r0, hp0 = tc * BHS_TILE_C + c0;
+    const int h1 = tr * BHS_TILE_R + r1, hp1 = tc * BHS_TILE_C + c1;
+    const bool ok0 = h0 < a.H && hp0 < a.H, ok1 = h1 < a.H && hp1 < a.H;
+    const int64_t npairs = (int64_t)a.B * a.B;
+    const int64_t p_begin = (int64_t)blockIdx.y * a.pairs_per_cta;
+    const int64_t p_end = min(npairs, p_begin + a.pairs_per_cta);
+    cplx* Asys = a.A + (int64_t)sys * a.sys_stride;
+    const cplx* rowf = a.rowf + (int64_t)sys * a.B * a.H;
+    const cplx* colf = a.colf + (int64_t)sys * a.B * a.H;
+    const cplx* diag = a.diag + (int64_t)sys * a.B * a.H;
+
+    for (int64_t pr = p_begin; pr < p_end; ++pr) {
+        const int b = (int)(pr / a.B), bp = (int)(pr % a.B);
+        cplx v0 = cmake(0.0, 0.0), v1 = cmake(0.0, 0.0);
+        if (b == bp) {
+            if (ok0 && h0 == hp0) v0 = diag[(int64_t)b * a.H + h0];
+            if (ok1 && h1 == hp1) v1 = diag[(int64_t)b * a.H + h1];
+        } else {
+            // S_{h''}(t) for the index window this tile references
+            const cplx* y2 = a.Y2 + pr * a.H2 + hd.sy_lo;
+            const cplx* hpw = a.hp + ((int64_t)sys * npairs + pr) * a.L2;
+            const int32_t* dg = a.deg2 + hd.sy_lo;
+            for (int j = tid; j < hd.sy_cnt; j += ASM_THREADS) s_sy[j] = cmul(y2[j], hpw[dg[j]]);
+            __syncthreads();
+            double ar0 = 0.0, ai0 = 0.0, ar1 = 0.0, ai1 = 0.0;
+            for (int t0 = 0; t0 < nt; t0 += nt_res) {
+                const int tn = min(nt_res, nt - t0);
+                if (!resident) {
+                    if (tid == 0) {
+                        fence_proxy_async();
+                        mbar_expect_tx(&bar, (uint32_t)(tn * (ASM_LAYER_COEF + ASM_LAYER_IDX)));
+                        tma_load_1d(s_coef, a.coef + hd.coef_off + (int64_t)t0 * BHS_TILE_E, (uint32_t)(tn * ASM_LAYER_COEF), &bar);
+                        tma_load_1d(s_idx, a.cidx + hd.idx_off + (int64_t)t0 * BHS_TILE_E, (uint32_t)(tn * ASM_LAYER_IDX), &bar);
+                    }
+                    mbar_wait(&bar, phase);
+                    phase ^= 1;
+                }
+#pragma unroll 4
+                for (int t = 0; t < tn; ++t) {
+                    const double cf0 = s_coef[t * BHS_TILE_E + e0], cf1 = s_coef[t * BHS_TILE_E + e1];
+                    const cplx s0 = s_sy[s_idx[t * BHS_TILE_E + e0]], s1 = s_sy[s_idx[t * BHS_TILE_E + e1]];
+                    ar0 = fma(cf0, s0.x, ar0); ai0 = fma(cf0, s0.y, ai0);
+                    ar1 = fma(cf1, s1.x, ar1); ai1 = fma(cf1, s1.y, ai1);
+                }
+                if (!resident) __syncthreads();  // everyone done with the chunk before it is overwritten
+            }
+            if (ok0) v0 = cmul(cmul(cmake(ar0, ai0), rowf[(int64_t)b * a.H + h0]), colf[(int64_t)bp * a.H + hp0]);
+            if (ok1) v1 = cmul(cmul(cmake(ar1, ai1), rowf[(int64_t)b * a.H + h1]), colf[(int64_t)bp * a.H + hp1]);
+        }
+        if (ok0) Asys[((int64_t)b * a.H + h0) * a.ld + (int64_t)bp * a.H + hp0] = v0;
+        if (ok1) Asys[((int64_t)b * a.H + h1) * a.ld + (int64_t)bp * a.H + hp1] = v1;
+        __syncthreads();  // s_sy reuse
+    }
+}
+
+// ---- host entries -------------------------------------------------------------------------------------------
+static inline int64_t al256(int64_t v) { return (v + 255) & ~(int64_t)255; }
+
+struct AsmWork {
+    double4* rad;
+    double* tv;
+    double* dist;
+    cplx* Y2;
+    cplx* hp;
+    cplx* rowf;
+    cplx* colf;
+    cplx* diag;
+    int64_t bytes;
+};
+static AsmWork carve(const bhs_plan* p, int B, int nsys, void* base) {
+    AsmWork w;
+    unsigned char* c = (unsigned char*)base;
+    int64_t np = (int64_t)B * B, off = 0;
+    auto take = [&](int64_t bytes) { unsigned char* r = c + off; off += al256(bytes); return r; };
+    w.rad = (double4*)take((int64_t)nsys * B * p->n_end * sizeof(double4));
+    w.tv = (double*)take(np * p->d * sizeof(double));
+    w.dist = (double*)take(np * sizeof(double));
+    w.Y2 = (cplx*)take(np * p->H2 * sizeof(cplx));
+    w.hp = (cplx*)take((int64_t)nsys * np * p->L2 * sizeof(cplx));
+    w.rowf = (cplx*)take((int64_t)nsys * B * p->H * sizeof(cplx));
+    w.colf = (cplx*)take((int64_t)nsys * B * p->H * sizeof(cplx));
+    w.diag = (cplx*)take((int64_t)nsys * B * p->H * sizeof(cplx));
+    w.bytes = off;
+    return w;
+}
+
+extern "C" int64_t bhs_assemble_workspace(const bhs_plan_t* plan, int B, int nsys) {
+    if (!plan || B <= 0 || nsys <= 0) return BHS_ERR_INVALID;
+    return carve(plan, B, nsys, nullptr).bytes;
+}
+
+static int run_factors(const bhs_plan* p, int B, int nsys, const double* d_radii, const double* d_k,
+                       const double* d_eta, const double* d_alpha, const double* d_beta, AsmWork& w, bool only_diag,
+                       cudaStream_t st) {
+    int rc = launch_ball_radial(p->d, p->n_end, B, nsys, d_radii, d_k, 0.0, w.rad, st);
+    if (rc) return rc;
+    int64_t tot = (int64_t)nsys * B * p->H;
+    factors_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(p->d, p->n_end, p->H, B, nsys, d_radii, d_k, d_eta,
+                                                                 (const cplx*)d_alpha, (const cplx*)d_beta, w.rad,
+                                                                 p->d_deg, only_diag ? nullptr : w.rowf,
+                                                                 only_diag ? nullptr : w.colf, w.diag);
+    BHS_CHECK_LAUNCH();
+    return BHS_OK;
+}
+
+int bhs_launch_harmonics_band2(const bhs_plan* plan, const double* d_xyz, int64_t npts, cplx* d_out, cudaStream_t st);
+
+extern "C" int bhs_assemble(const bhs_plan_t* plan, int B, int nsys, const double* d_centers, const double* d_radii,
+                            const double* d_k, const double* d_eta, const double* d_alpha, const double* d_beta,
+                            double* d_A, int64_t ld, int64_t sys_stride, void* d_work, void* stream) {
+    if (!plan || B <= 0 || nsys <= 0 || !d_centers || !d_radii || !d_k || !d_A || !d_work) return BHS_ERR_INVALID;
+    const int64_t N = (int64_t)B * plan->H;
+    if (ld < N) return BHS_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    AsmWork w = carve(plan, B, nsys, d_work);
+    int rc = run_factors(plan, B, nsys, d_radii, d_k, d_eta, d_alpha, d_beta, w, false, st);
+    if (rc) return rc;
+    const int64_t np = (int64_t)B * B;
+    pair_vectors_kernel<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(plan->d, B, d_centers, w.tv, w.dist);
+    BHS_CHECK_LAUNCH();
+    rc = bhs_harmonics(plan, 1, w.tv, np, (double*)w.Y2, stream);
+    if (rc) return rc;
+    {
+        const int d = plan->d;
+        int shift = (d & 1) ? (d - 3) / 2 : d / 2 - 1;
+        int n_store = plan->L2 + 1 + shift;
+        int T = 64;
+        while (T > 32 && (size_t)2 * n_store * T * sizeof(double) > 160 * 1024) T >>= 1;
+        size_t smem = (size_t)2 * n_store * T * sizeof(double);
+        if (smem > 200 * 1024) return BHS_ERR_UNSUPPORTED;
+        cudaFuncSetAttribute(pair_radial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int64_t total = np * nsys, blocks = (total + T - 1) / T;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        pair_radial_kernel<<<(unsigned)blocks, T, smem, st>>>(d, plan->L2, n_store, B, nsys, d_k, w.dist, w.hp);
+        BHS_CHECK_LAUNCH();
+    }
+    AsmArgs a;
+    a.B = B; a.H = plan->H; a.H2 = plan->H2; a.L2 = plan->L2;
+    a.tiles = plan->d_tiles; a.coef = plan->d_coef; a.cidx = plan->d_cidx; a.deg2 = plan->d_deg2;
+    a.Y2 = w.Y2; a.hp = w.hp; a.rowf = w.rowf; a.colf = w.colf; a.diag = w.diag;
+    a.A = (cplx*)d_A; a.ld = ld; a.sys_stride = sys_stride;
+    // shared-memory budget: SY window (worst case H2 entries) + resident coefficient layers
+    const size_t budget = 200 * 1024;
+    size_t sy_bytes = ((size_t)plan->H2 * sizeof(cplx) + 127) & ~(size_t)127;
+    if (sy_bytes + (ASM_LAYER_COEF + ASM_LAYER_IDX) > budget) return BHS_ERR_UNSUPPORTED;
+    int nt_cap = (int)((budget - sy_bytes) / (ASM_LAYER_COEF + ASM_LAYER_IDX));
+    a.nt_res = plan->max_nt < nt_cap ? (plan->max_nt > 0 ? plan->max_nt : 1) : nt_cap;
+    size_t smem = (size_t)a.nt_res * (ASM_LAYER_COEF + ASM_LAYER_IDX) + sy_bytes;
+    cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int ntiles = plan->tiles_r * plan->tiles_c;
+    // pair chunks: enough CTAs to fill the machine a few times over, at least 8 pairs per CTA
+    int64_t want_ctas = 148 * 8;
+    int64_t chunks = (want_ctas + (int64_t)ntiles * nsys - 1) / ((int64_t)ntiles * nsys);
+    if (chunks < 1) chunks = 1;
+    int64_t ppc = (np + chunks - 1) / chunks;
+    if (ppc < 8) ppc = 8;
+    if (ppc > np) ppc = np;
+    chunks = (np + ppc - 1) / ppc;
+    a.pairs_per_cta = (int)ppc;
+    if (chunks > 65535 || nsys > 65535) return BHS_ERR_UNSUPPORTED;
+    dim3 grid((unsigned)ntiles, (unsigned)chunks, (unsigned)nsys);
+    assemble_kernel<<<grid, ASM_THREADS, smem, st>>>(a);
+    BHS_CHECK_LAUNCH();
+    return BHS_OK;
+}
+
+extern "C" int bhs_diag_coef(const bhs_plan_t* plan, int B, int nsys, const double* d_radii, const double* d_k,
+                             const double* d_eta, const double* d_alpha, const double* d_beta, double* d_out,
+                             void* stream) {
+    if (!plan || B <= 0 || nsys <= 0 || !d_radii || !d_k || !d_out) return BHS_ERR_INVALID;
+    // needs only the radial table: carve it out of a temporary allocation
+    cudaStream_t st = (cudaStream_t)stream;
+    double4* rad = nullptr;
+    if (cudaMallocAsync((void**)&rad, (size_t)nsys * B * plan->n_end * sizeof(double4), st) != cudaSuccess)
+        return BHS_ERR_ALLOC;
+    AsmWork w;
+    w.rad = rad; w.rowf = nullptr; w.colf = nullptr; w.diag = (cplx*)d_out;
+    int rc = run_factors(plan, B, nsys, d_radii, d_k, d_eta, d_alpha, d_beta, w, true, st);
+    cudaFreeAsync(rad, st);
+    return rc;
+}
+
+// ---- K3: right-hand side ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) rhs_expand_kernel(int d, int B, int H, int Q, const cplx* __restrict__ g,
+                                                         const double* __restrict__ centers,
+                                                         const double* __restrict__ radii,
+                                                         const double* __restrict__ k_in,
+                                                         const double* __restrict__ dir, const cplx* __restrict__ alpha,
+                                                         const cplx* __restrict__ beta, const double* __restrict__ qdirs,
+                                                         const cplx* __restrict__ WY, cplx* __restrict__ out) {
+    extern __shared__ __align__(16) cplx s_g[];  // [Q]
+    const int b = blockIdx.y, s = blockIdx.z;
+    for (int q = threadIdx.x; q < Q; q += blockDim.x) {
+        cplx v;
+        if (g) {
+            v = g[((int64_t)s * Q + q) * B + b];
+        } else {
+            double k = k_in[s], rho = radii[b];
+            double dy = 0.0, dc = 0.0;
+            for (int a = 0; a < d; ++a) {
+                dy += dir[a] * qdirs[(int64_t)a * Q + q];
+                dc += dir[a] * centers[(int64_t)b * d + a];
+            }
+            double ph = k * (rho * dy + dc), sn, co;
+            sincos(ph, &sn, &co);
+            cplx u = cmake(co, sn);
+            cplx al = alpha ? alpha[b] : cmake(1.0, 0.0);
+            cplx be = beta ? beta[b] : cmake(0.0, 0.0);
+            // -alpha u - beta (i k d.y) u
+            cplx t = cadd(al, cmul(be, cmake(0.0, k * dy)));
+            v = cmul(cmake(-t.x, -t.y), u);
+        }
+        s_g[q] = v;
+    }
+    __syncthreads();
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= H) return;
+    double ar = 0.0, ai = 0.0;
+    for (int q = 0; q < Q; ++q) {
+        cplx w = WY[(int64_t)q * H + h], gv = s_g[q];
+        ar = fma(gv.x, w.x, ar); ar = fma(-gv.y, w.y, ar);
+        ai = fma(gv.x, w.y, ai); ai = fma(gv.y, w.x, ai);
+    }
+    out[((int64_t)s * B + b) * H + h] = cmake(ar, ai);
+}
+
+extern "C" int bhs_rhs_expand(const bhs_plan_t* plan, int B, int nsys, const double* d_g, const double* d_centers,
+                              const double* d_radii, const double* d_k_in, const double* d_dir, const double* d_alpha,
+                              const double* d_beta, double* d_out, void* stream) {
+    if (!plan || B <= 0 || nsys <= 0 || !d_out) return BHS_ERR_INVALID;
+    if (!d_g && (!d_centers || !d_radii || !d_k_in || !d_dir)) return BHS_ERR_INVALID;
+    if (nsys > 65535 || B > 65535) return BHS_ERR_UNSUPPORTED;
+    size_t smem = (size_t)plan->Q * sizeof(cplx);
+    if (smem > 200 * 1024) return BHS_ERR_UNSUPPORTED;
+    cudaFuncSetAttribute(rhs_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 grid((plan->H + 127) / 128, B, nsys);
+    rhs_expand_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(plan->d, B, plan->H, plan->Q, (const cplx*)d_g,
+                                                                 d_centers, d_radii, d_k_in, d_dir,
+                                                                 (const cplx*)d_alpha, (const cplx*)d_beta,
+                                                                 plan->d_qdirs, plan->d_WY, (cplx*)d_out);
+    BHS_CHECK_LAUNCH();
+    return BHS_OK;
+}

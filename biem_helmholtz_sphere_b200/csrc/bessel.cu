@@ -1,0 +1,141 @@
+// K1: batch hyperspherical Bessel / Hankel functions, orders 0..n_max, complex128 output.
+//
+// One thread per argument runs the recurrences with its order sequence held in shared memory
+// (order-major, thread-minor: conflict-free); the block then streams its contiguous
+// [args, n_max+1] slab out with coalesced 16-byte stores.
+// Replaces ultrasphere.shn1 / potential_coef radial factors (_biem.py:439,447,654-685,723-741,896-914).
+#include "special.cuh"
+
+struct StridedArr {
+    double* base;
+    int stride;
+    __device__ __forceinline__ double& operator[](int n) const { return base[(size_t)n * stride]; }
+};
+
+__global__ void bessel_kernel(int d, int kind, int derivative, int n_max, int n_store, const double* __restrict__ x,
+                              int64_t nx, cplx* __restrict__ out) {
+    extern __shared__ __align__(16) double sm[];
+    const int T = blockDim.x;
+    StridedArr aj{sm + threadIdx.x, T};
+    StridedArr ay{sm + (size_t)n_store * T + threadIdx.x, T};
+    const bool want_j = kind != BHS_KIND_Y, want_y = kind != BHS_KIND_J;
+    for (int64_t i0 = (int64_t)blockIdx.x * T; i0 < nx; i0 += (int64_t)gridDim.x * T) {
+        int64_t i = i0 + threadIdx.x;
+        double xv = (i < nx) ? x[i] : 1.0;
+        radial_sequence(d, xv, n_max + 1, aj, ay, want_j, want_y);
+        if (derivative) {
+            for (int n = 0; n <= n_max; ++n) {
+                if (want_j) aj[n] = radial_deriv(n, xv, aj[n], aj[n + 1]);
+                if (want_y) ay[n] = radial_deriv(n, xv, ay[n], ay[n + 1]);
+            }
+        }
+        __syncthreads();
+        int64_t cnt = nx - i0;
+        if (cnt > T) cnt = T;
+        int64_t total = cnt * (n_max + 1);
+        for (int64_t e = threadIdx.x; e < total; e += T) {
+            int t = (int)(e / (n_max + 1)), n = (int)(e % (n_max + 1));
+            double re = want_j ? sm[(size_t)n * T + t] : sm[((size_t)n_store + n) * T + t];
+            double im = (kind == BHS_KIND_H1) ? sm[((size_t)n_store + n) * T + t] : 0.0;
+            out[i0 * (n_max + 1) + e] = cmake(re, im);
+        }
+        __syncthreads();
+    }
+}
+
+extern "C" int bhs_bessel(int d, int kind, int derivative, int n_max, const double* d_x, int64_t nx, double* d_out,
+                          void* stream) {
+    if (d < 2 || kind < 0 || kind > 2 || n_max < 0 || nx < 0 || !d_x || !d_out) return BHS_ERR_INVALID;
+    if (nx == 0) return BHS_OK;
+    int shift = (d & 1) ? (d - 3) / 2 : d / 2 - 1;
+    int n_store = n_max + 2 + shift + 1;
+    int T = 128;
+    while (T > 32 && (size_t)2 * n_store * T * sizeof(double) > 160 * 1024) T >>= 1;
+    size_t smem = (size_t)2 * n_store * T * sizeof(double);
+    if (smem > 200 * 1024) return BHS_ERR_UNSUPPORTED;
+    cudaFuncSetAttribute(bessel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int64_t blocks = (nx + T - 1) / T;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    bessel_kernel<<<(unsigned)blocks, T, smem, (cudaStream_t)stream>>>(d, kind, derivative, n_max, n_store, d_x, nx,
+                                                                       (cplx*)d_out);
+    BHS_CHECK_LAUNCH();
+    return BHS_OK;
+}
+
+// ---- FP64 peak micro-benchmarks ---------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dfma_peak_kernel(int iters, double* sink) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 0.999999, c = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll 4
+        for (int u = 0; u < 4; ++u) {
+            a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+            a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+        }
+    }
+    double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 123.456) sink[0] = s;
+}
+
+__global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double* sink) {
+    double a = 1.0 + threadIdx.x * 1e-9, b = 0.5;
+    double c[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i] = 0.0;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[2 * u]), "+d"(c[2 * u + 1])
+                         : "d"(a), "d"(b));
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += c[i];
+    if (s == 123.456) sink[0] = s;
+}
+
+extern "C" int bhs_fp64_peak(int shape, int iters, double* tflops_out) {
+    if (!tflops_out || iters <= 0 || shape < 0 || shape > 1) return BHS_ERR_INVALID;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    double* sink = nullptr;
+    if (cudaMalloc(&sink, 8) != cudaSuccess) return BHS_ERR_ALLOC;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int blocks = sms * 4, threads = 256;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0);
+        if (shape == 0) dfma_peak_kernel<<<blocks, threads>>>(iters, sink);
+        else dmma_peak_kernel<<<blocks, threads>>>(iters, sink);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double flops = (shape == 0) ? (double)blocks * threads * iters * 32.0 * 2.0
+                                    : (double)blocks * (threads / 32) * iters * 8.0 * 512.0;
+        double tf = flops / (ms * 1e-3) * 1e-12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    *tflops_out = best;
+    return BHS_OK;
+}
+
+extern "C" int bhs_version(void) { return 100; }
+extern "C" int bhs_device_sm_count(int* out) {
+    if (!out) return BHS_ERR_INVALID;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaDeviceGetAttribute(out, cudaDevAttrMultiProcessorCount, dev);
+    return e == cudaSuccess ? BHS_OK : (int)e;
+}

@@ -1,0 +1,734 @@
+// K5: dense complex128 solve  A x = f  (row-major), replacing batch_tensorsolve.btensorsolve -> zgesv
+// (_biem.py:797).
+//
+// Right-looking recursive blocked LU with TOURNAMENT partial pivoting (CALU): per 32-column panel the
+// pivot rows are chosen by a reduction tree of register-resident Gaussian eliminations (128 rows per
+// CTA, one row per thread), so no step of the factorisation needs a grid-wide sync.  Outer blocks are
+// 128 wide; all Schur-complement work (inside and outside the outer block) is one kernel:
+//
+//   zgemm_sub_kernel :  C -= A * B  on FP64 tensor cores (mma.sync m8n8k4.f64 -> SASS DMMA.8x8x4), complex
+//   arithmetic through the real embedding  [ar ai] x [[br bi],[-bi br]], operands pre-packed by the
+//   triangular-solve kernels into the exact shared-memory image (padded, conflict-free) so that every
+//   pipeline stage is two 1-D TMA bulk copies (cp.async.bulk + mbarrier), 3 stages deep.
+#include "common.cuh"
+
+#define LU_NB 32     // panel width
+#define LU_NBO 128   // outer block width
+#define LU_R 128     // rows per tournament CTA
+#define G_TM 64
+#define G_TN 64
+#define G_KC 8
+#define G_LDS 20
+#define G_A_STAGE (G_TM * G_LDS)
+#define G_B_STAGE (2 * G_TN * G_LDS)
+#define G_STAGES 3
+#define G_THREADS 128
+
+static inline int64_t al256(int64_t v) { return (v + 255) & ~(int64_t)255; }
+static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// =====================================================================================================
+// GEMM:  C[rows, cols] -= Lp * Up
+// =====================================================================================================
+struct GemmArgs {
+    const double* Lp;
+    const double* Up;
+    int nks_total;  // packed stages per tile (pitch of both packed buffers)
+    int ks0, nks;   // stage window used by this product
+    cplx* C;
+    int64_t ldc;
+    int64_t row_base, col_base;  // global row / col of packed tile (0, 0)
+    int rt0, ct0;                // first row / col tile of this launch
+    int64_t row_lo, row_hi, col_lo, col_hi;  // output window (global indices, half open)
+};
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(G_THREADS, 2) zgemm_sub_kernel(GemmArgs g) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full[G_STAGES];
+    double* smA = reinterpret_cast<double*>(smem_raw);
+    double* smB = smA + G_STAGES * G_A_STAGE;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 1, wn = warp & 1;
+    const int rt = g.rt0 + blockIdx.y, ct = g.ct0 + blockIdx.x;
+    const double* Lt = g.Lp + ((int64_t)rt * g.nks_total + g.ks0) * G_A_STAGE;
+    const double* Ut = g.Up + ((int64_t)ct * g.nks_total + g.ks0) * G_B_STAGE;
+    if (tid == 0) {
+        for (int s = 0; s < G_STAGES; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int s = 0; s < G_STAGES && s < g.nks; ++s) {
+            mbar_expect_tx(&full[s], (uint32_t)((G_A_STAGE + G_B_STAGE) * sizeof(double)));
+            tma_load_1d(smA + s * G_A_STAGE, Lt + (int64_t)s * G_A_STAGE, G_A_STAGE * sizeof(double), &full[s]);
+            tma_load_1d(smB + s * G_B_STAGE, Ut + (int64_t)s * G_B_STAGE, G_B_STAGE * sizeof(double), &full[s]);
+        }
+    }
+    // accumulators <- C
+    double acc[4][8][2];
+    const int64_t row0 = g.row_base + (int64_t)rt * G_TM + wm * 32 + (lane >> 2);
+    const int64_t col0 = g.col_base + (int64_t)ct * G_TN + wn * 32 + (lane & 3);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t r = row0 + 8 * i;
+        const bool rv = r >= g.row_lo && r < g.row_hi;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int64_t c = col0 + 4 * j;
+            cplx v = cmake(0.0, 0.0);
+            if (rv && c >= g.col_lo && c < g.col_hi) v = g.C[r * g.ldc + c];
+            acc[i][j][0] = v.x;
+            acc[i][j][1] = v.y;
+        }
+    }
+    const int a_off = (wm * 32 + (lane >> 2)) * G_LDS + (lane & 3);
+    const int b_off = (wn * 64 + (lane >> 2)) * G_LDS + (lane & 3);
+    for (int it = 0; it < g.nks; ++it) {
+        const int s = it % G_STAGES;
+        mbar_wait(&full[s], (it / G_STAGES) & 1);
+        const double* As = smA + s * G_A_STAGE + a_off;
+        const double* Bs = smB + s * G_B_STAGE + b_off;
+#pragma unroll
+        for (int k4 = 0; k4 < (2 * G_KC) / 4; ++k4) {
+            double a[4], b[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[i * 8 * G_LDS + 4 * k4];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) b[j] = Bs[j * 8 * G_LDS + 4 * k4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        __syncthreads();
+        if (tid == 0 && it + G_STAGES < g.nks) {
+            fence_proxy_async();
+            mbar_expect_tx(&full[s], (uint32_t)((G_A_STAGE + G_B_STAGE) * sizeof(double)));
+            tma_load_1d(smA + s * G_A_STAGE, Lt + (int64_t)(it + G_STAGES) * G_A_STAGE, G_A_STAGE * sizeof(double), &full[s]);
+            tma_load_1d(smB + s * G_B_STAGE, Ut + (int64_t)(it + G_STAGES) * G_B_STAGE, G_B_STAGE * sizeof(double), &full[s]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t r = row0 + 8 * i;
+        const bool rv = r >= g.row_lo && r < g.row_hi;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int64_t c = col0 + 4 * j;
+            if (rv && c >= g.col_lo && c < g.col_hi) g.C[r * g.ldc + c] = cmake(acc[i][j][0], acc[i][j][1]);
+        }
+    }
+}
+
+static const size_t G_SMEM = (size_t)G_STAGES * (G_A_STAGE + G_B_STAGE) * sizeof(double);
+static const size_t LU_TILE_SMEM = (size_t)LU_R * (LU_NB + 1) * sizeof(cplx);
+
+// ---- packing -------------------------------------------------------------------------------------------
+// Lp tile (rt, stage): [64 rows][20] doubles, row r = interleaved complex A[row_base + 64 rt + r][k0 + 8 stage ..]
+__global__ void pack_l_kernel(const cplx* __restrict__ A, int64_t ld, int64_t N, int64_t row_base, int64_t r_begin,
+                              int64_t r_end_pad, int64_t k0, int K, int Kpad, double* __restrict__ Lp, int nks_total,
+                              int ks_off) {
+    // thread -> (row, kc); kc fastest
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t nrows = r_end_pad - r_begin;
+    if (idx >= nrows * Kpad) return;
+    int kc = (int)(idx % Kpad);
+    int64_t r = r_begin + idx / Kpad;
+    cplx v = cmake(0.0, 0.0);
+    if (r < N && kc < K) v = A[r * ld + k0 + kc];
+    int64_t rel = r - row_base;
+    int64_t rt = rel / G_TM;
+    int rr = (int)(rel % G_TM);
+    double* dst = Lp + (((int64_t)rt * nks_total + ks_off + kc / G_KC) * G_TM + rr) * G_LDS + 2 * (kc % G_KC);
+    *reinterpret_cast<double2*>(dst) = v;
+}
+// Up tile (ct, stage): [128 real cols][20] doubles: row 2j: (-br, +bi) pairs, row 2j+1: (-bi, -br)
+__global__ void pack_u_kernel(const cplx* __restrict__ A, int64_t ld, int64_t ncols_total, int64_t k_row0, int K,
+                              int Kpad, int64_t c_begin, int64_t c_end_pad, double* __restrict__ Up, int nks_total,
+                              int ks_off) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t ncols = c_end_pad - c_begin;
+    if (idx >= ncols * Kpad) return;
+    int64_t c = c_begin + idx % ncols;
+    int p = (int)(idx / ncols);
+    cplx v = cmake(0.0, 0.0);
+    if (c < ncols_total && p < K) v = A[(k_row0 + p) * ld + c];
+    int64_t ct = c / G_TN;
+    int jj = (int)(c % G_TN);
+    double* base = Up + (((int64_t)ct * nks_total + ks_off + p / G_KC) * (2 * G_TN)) * G_LDS + 2 * (p % G_KC);
+    *reinterpret_cast<double2*>(base + (int64_t)(2 * jj) * G_LDS) = make_double2(-v.x, v.y);
+    *reinterpret_cast<double2*>(base + (int64_t)(2 * jj + 1) * G_LDS) = make_double2(-v.y, -v.x);
+}
+
+// =====================================================================================================
+// Tournament pivot selection
+// =====================================================================================================
+// One CTA eliminates up to LU_R candidate rows (one per thread, LU_NB complex in registers) with partial
+// pivoting and emits the rows it pivoted on, in order.  rows_in == nullptr: contiguous rows
+// [row_begin + 128*blockIdx.x, ...) ; otherwise rows_in[128*blockIdx.x + t] (-1 = empty slot).
+__global__ void __launch_bounds__(LU_R) lu_select_kernel(const cplx* __restrict__ A, int64_t ld, int64_t col0, int w,
+                                                         const int32_t* __restrict__ rows_in, int64_t n_in,
+                                                         int64_t row_begin, int64_t row_end,
+                                                         int32_t* __restrict__ rows_out) {
+    extern __shared__ __align__(16) unsigned char lu_dyn_smem[];
+    cplx (*tile)[LU_NB + 1] = reinterpret_cast<cplx (*)[LU_NB + 1]>(lu_dyn_smem);
+    __shared__ cplx prow[LU_NB];
+    __shared__ double wmag[LU_R / 32];
+    __shared__ int wlane[LU_R / 32];
+    __shared__ int s_rows[LU_R];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // which global row does this thread own?
+    int64_t slot = (int64_t)blockIdx.x * LU_R + tid;
+    int32_t myrow = -1;
+    if (rows_in) {
+        if (slot < n_in) myrow = rows_in[slot];
+    } else {
+        int64_t r = row_begin + slot;
+        if (r < row_end) myrow = (int32_t)r;
+    }
+    s_rows[tid] = myrow;
+    __syncthreads();
+    // coalesced load: each warp reads whole rows
+    for (int rr = warp; rr < LU_R; rr += LU_R / 32) {
+        int32_t gr = s_rows[rr];
+        cplx v = cmake(0.0, 0.0);
+        if (gr >= 0 && lane < w) v = A[(int64_t)gr * ld + col0 + lane];
+        tile[rr][lane] = v;
+    }
+    __syncthreads();
+    cplx x[LU_NB];
+#pragma unroll
+    for (int c = 0; c < LU_NB; ++c) x[c] = tile[tid][c];
+    bool active = myrow >= 0;
+#pragma unroll
+    for (int c = 0; c < LU_NB; ++c) {
+        if (c < w) {
+            double mag = active ? fabs(x[c].x) + fabs(x[c].y) : -1.0;
+            int bl = lane;
+            double bm = mag;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                double om = __shfl_xor_sync(0xffffffffu, bm, o);
+                int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+                if (om > bm || (om == bm && ol < bl)) { bm = om; bl = ol; }
+            }
+            if (lane == 0) { wmag[warp] = bm; wlane[warp] = bl; }
+            __syncthreads();
+            int bw = 0;
+            double best = wmag[0];
+#pragma unroll
+            for (int q = 1; q < LU_R / 32; ++q)
+                if (wmag[q] > best) { best = wmag[q]; bw = q; }
+            const int winner = bw * 32 + wlane[bw];
+            const bool any = best >= 0.0;  // at least one active row left
+            if (any && tid == winner) {
+#pragma unroll
+                for (int j = 0; j < LU_NB; ++j) prow[j] = x[j];
+                rows_out[(int64_t)blockIdx.x * LU_NB + c] = myrow;
+                active = false;
+            }
+            if (!any && tid == 0) rows_out[(int64_t)blockIdx.x * LU_NB + c] = -1;
+            __syncthreads();
+            if (any && active && best > 0.0) {
+                const cplx l = cdiv(x[c], prow[c]);
+#pragma unroll
+                for (int j = c + 1; j < LU_NB; ++j) x[j] = cfma(cmake(-l.x, -l.y), prow[j], x[j]);
+            }
+        } else {
+            if (tid == 0) rows_out[(int64_t)blockIdx.x * LU_NB + c] = -1;
+        }
+    }
+}
+
+// Convert the ordered pivot-row list of a panel into LAPACK-style sequential swaps ipiv[j + c].
+__global__ void lu_pivots_kernel(const int32_t* __restrict__ cand, int64_t j, int w, int32_t* __restrict__ ipiv) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int32_t piv[LU_NB];
+    for (int c = 0; c < w; ++c) {
+        int32_t loc = cand[c];
+        if (loc < 0) loc = (int32_t)(j + c);  // cannot happen for a square matrix; keep the row in place
+        // follow the earlier swaps of this panel
+        for (int q = 0; q < c; ++q) {
+            int32_t a = (int32_t)(j + q), b = piv[q];
+            if (loc == a) loc = b;
+            else if (loc == b) loc = a;
+        }
+        piv[c] = loc;
+        ipiv[j + c] = loc;
+    }
+}
+
+// Apply the swaps of one panel to `ncols` contiguous columns of a row-major array (matrix or rhs).
+__global__ void lu_swap_kernel(cplx* __restrict__ M, int64_t ld, int64_t ncols, const int32_t* __restrict__ ipiv,
+                               int64_t j, int w) {
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncols) return;
+    for (int q = 0; q < w; ++q) {
+        int64_t a = j + q, b = ipiv[j + q];
+        if (a != b) {
+            cplx va = M[a * ld + c], vb = M[b * ld + c];
+            M[a * ld + c] = vb;
+            M[b * ld + c] = va;
+        }
+    }
+}
+
+// Unpivoted LU of the w x w diagonal block (single CTA, 256 threads), in place.
+__global__ void __launch_bounds__(256) lu_diag_kernel(cplx* __restrict__ A, int64_t ld, int64_t j, int w,
+                                                      int32_t* __restrict__ info) {
+    __shared__ cplx t[LU_NB][LU_NB + 1];
+    const int tid = threadIdx.x;
+    for (int e = tid; e < w * w; e += 256) t[e / w][e % w] = A[(j + e / w) * ld + j + e % w];
+    __syncthreads();
+    for (int c = 0; c < w; ++c) {
+        cplx p = t[c][c];
+        if (p.x == 0.0 && p.y == 0.0) {
+            if (tid == 0) atomicCAS(info, 0, (int)(j + c + 1));
+            __syncthreads();
+            continue;
+        }
+        cplx ip = crecip(p);
+        __syncthreads();
+        for (int r = c + 1 + tid; r < w; r += 256) t[r][c] = cmul(t[r][c], ip);
+        __syncthreads();
+        int rem = w - c - 1;
+        for (int e = tid; e < rem * rem; e += 256) {
+            int r = c + 1 + e / rem, q = c + 1 + e % rem;
+            t[r][q] = cfma(cmake(-t[r][c].x, -t[r][c].y), t[c][q], t[r][q]);
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < w * w; e += 256) A[(j + e / w) * ld + j + e % w] = t[e / w][e % w];
+}
+
+// L21 = A21 U11^{-1}: one row per thread (registers), U11 in shared memory.  Also emits the packed
+// GEMM image of the new L columns (rows below the diagonal block).
+__global__ void __launch_bounds__(LU_R) lu_l21_kernel(cplx* __restrict__ A, int64_t ld, int64_t N, int64_t j, int w) {
+    extern __shared__ __align__(16) unsigned char lu_dyn_smem[];
+    cplx (*tile)[LU_NB + 1] = reinterpret_cast<cplx (*)[LU_NB + 1]>(lu_dyn_smem);
+    __shared__ cplx U[LU_NB][LU_NB + 1];
+    __shared__ cplx rdiag[LU_NB];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t r0 = j + w + (int64_t)blockIdx.x * LU_R;
+    for (int e = tid; e < LU_NB * LU_NB; e += LU_R) {
+        int r = e / LU_NB, c = e % LU_NB;
+        U[r][c] = (r < w && c < w && c >= r) ? A[(j + r) * ld + j + c] : cmake(0.0, 0.0);
+    }
+    for (int rr = warp; rr < LU_R; rr += LU_R / 32) {
+        int64_t gr = r0 + rr;
+        tile[rr][lane] = (gr < N && lane < w) ? A[gr * ld + j + lane] : cmake(0.0, 0.0);
+    }
+    __syncthreads();
+    if (tid < LU_NB) {
+        cplx d = U[tid][tid];
+        rdiag[tid] = (tid < w && (d.x != 0.0 || d.y != 0.0)) ? crecip(d) : cmake(0.0, 0.0);
+    }
+    __syncthreads();
+    cplx x[LU_NB];
+#pragma unroll
+    for (int c = 0; c < LU_NB; ++c) x[c] = tile[tid][c];
+#pragma unroll
+    for (int c = 0; c < LU_NB; ++c) {
+        // x[c] = (a[c] - sum_{q<c} x[q] U[q][c]) / U[c][c]
+        cplx s = x[c];
+#pragma unroll
+        for (int q = 0; q < c; ++q) s = cfma(cmake(-x[q].x, -x[q].y), U[q][c], s);
+        x[c] = cmul(s, rdiag[c]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < LU_NB; ++c) tile[tid][c] = x[c];
+    __syncthreads();
+    for (int rr = warp; rr < LU_R; rr += LU_R / 32) {
+        int64_t gr = r0 + rr;
+        if (gr < N && lane < w) A[gr * ld + j + lane] = tile[rr][lane];
+    }
+}
+
+// U12 = L11^{-1} A12 for a 32-row block: one column per thread (registers), L11 (unit lower) in smem.
+__global__ void __launch_bounds__(128) lu_trsm32_kernel(cplx* __restrict__ A, int64_t ld, int64_t j, int w,
+                                                        cplx* __restrict__ X, int64_t ldx, int64_t c_begin,
+                                                        int64_t c_end) {
+    __shared__ cplx Ls[LU_NB][LU_NB + 1];
+    const int tid = threadIdx.x;
+    for (int e = tid; e < LU_NB * LU_NB; e += 128) {
+        int r = e / LU_NB, c = e % LU_NB;
+        Ls[r][c] = (r < w && c < r) ? A[(j + r) * ld + j + c] : cmake(0.0, 0.0);
+    }
+    __syncthreads();
+    int64_t c = c_begin + (int64_t)blockIdx.x * 128 + tid;
+    if (c >= c_end) return;
+    cplx x[LU_NB];
+#pragma unroll
+    for (int r = 0; r < LU_NB; ++r) x[r] = (r < w) ? X[(j + r) * ldx + c] : cmake(0.0, 0.0);
+#pragma unroll
+    for (int r = 1; r < LU_NB; ++r) {
+        cplx s = x[r];
+#pragma unroll
+        for (int q = 0; q < r; ++q) s = cfma(cmake(-Ls[r][q].x, -Ls[r][q].y), x[q], s);
+        x[r] = s;
+    }
+#pragma unroll
+    for (int r = 0; r < LU_NB; ++r)
+        if (r < w) X[(j + r) * ldx + c] = x[r];
+}
+
+// =====================================================================================================
+// right-hand-side kernels (few columns): y -= L * x style updates and triangular block solves
+// =====================================================================================================
+// rhs[r, :] -= sum_{q<K} M[r, k0+q] * rhs[k0+q, :]   for r in [r_begin, r_end): one warp per row
+__global__ void __launch_bounds__(256) rhs_gemv_sub_kernel(const cplx* __restrict__ M, int64_t ld, int64_t r_begin,
+                                                           int64_t r_end, int64_t k0, int K, cplx* __restrict__ rhs,
+                                                           int nrhs) {
+    const int lane = threadIdx.x & 31;
+    int64_t r = r_begin + (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= r_end) return;
+    for (int c = 0; c < nrhs; ++c) {
+        double sr = 0.0, si = 0.0;
+        for (int q = lane; q < K; q += 32) {
+            cplx m = M[r * ld + k0 + q], v = rhs[(k0 + q) * nrhs + c];
+            sr += m.x * v.x - m.y * v.y;
+            si += m.x * v.y + m.y * v.x;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            sr += __shfl_xor_sync(0xffffffffu, sr, o);
+            si += __shfl_xor_sync(0xffffffffu, si, o);
+        }
+        if (lane == 0) {
+            cplx v = rhs[r * nrhs + c];
+            rhs[r * nrhs + c] = cmake(v.x - sr, v.y - si);
+        }
+    }
+}
+// Solve the T x T diagonal block at k0 against rhs rows [k0, k0+T): lower-unit (forward) or upper (backward).
+__global__ void __launch_bounds__(128) rhs_block_solve_kernel(const cplx* __restrict__ M, int64_t ld, int64_t k0, int T,
+                                                              int upper, cplx* __restrict__ rhs, int nrhs) {
+    __shared__ cplx v[LU_NBO];
+    const int tid = threadIdx.x;
+    for (int c = 0; c < nrhs; ++c) {
+        if (tid < T) v[tid] = rhs[(k0 + tid) * nrhs + c];
+        __syncthreads();
+        if (!upper) {
+            for (int q = 0; q < T; ++q) {
+                cplx xq = v[q];
+                if (tid > q && tid < T) v[tid] = cfma(cmake(-M[(k0 + tid) * ld + k0 + q].x, -M[(k0 + tid) * ld + k0 + q].y), xq, v[tid]);
+                __syncthreads();
+            }
+        } else {
+            for (int q = T - 1; q >= 0; --q) {
+                if (tid == q) {
+                    cplx dg = M[(k0 + q) * ld + k0 + q];
+                    v[q] = (dg.x != 0.0 || dg.y != 0.0) ? cdiv(v[q], dg) : v[q];
+                }
+                __syncthreads();
+                cplx xq = v[q];
+                if (tid < q) v[tid] = cfma(cmake(-M[(k0 + tid) * ld + k0 + q].x, -M[(k0 + tid) * ld + k0 + q].y), xq, v[tid]);
+                __syncthreads();
+            }
+        }
+        if (tid < T) rhs[(k0 + tid) * nrhs + c] = v[tid];
+        __syncthreads();
+    }
+}
+// permutation from sequential swaps, applied to a few columns (used by the stand-alone zgetrs)
+__global__ void rhs_apply_ipiv_kernel(const int32_t* __restrict__ ipiv, int64_t N, cplx* __restrict__ rhs, int nrhs) {
+    if (blockIdx.x != 0) return;
+    int c = threadIdx.x;
+    if (c >= nrhs) return;
+    for (int64_t i = 0; i < N; ++i) {
+        int64_t p = ipiv[i];
+        if (p != i) {
+            cplx a = rhs[i * nrhs + c], b = rhs[p * nrhs + c];
+            rhs[i * nrhs + c] = b;
+            rhs[p * nrhs + c] = a;
+        }
+    }
+}
+
+// =====================================================================================================
+// host driver
+// =====================================================================================================
+struct LuCtx {
+    cplx* A;
+    int64_t ld, N;
+    cplx* rhs;  // may be null
+    int nrhs;
+    int32_t* ipiv;
+    int32_t* info;
+    int32_t* cand[2];
+    double* Lp;
+    double* Up;
+    int nks_total;      // LU_NBO / G_KC
+    int64_t J;          // current outer block start (anchor of Lp rows and of the stage index)
+    cudaStream_t st;
+    int err;
+};
+
+struct LuWork {
+    int32_t* cand0;
+    int32_t* cand1;
+    double* Lp;
+    double* Up;
+    int64_t bytes;
+};
+static LuWork lu_carve(int64_t N, void* base) {
+    LuWork w;
+    unsigned char* c = (unsigned char*)base;
+    int64_t off = 0;
+    auto take = [&](int64_t b) { unsigned char* r = c + off; off += al256(b); return r; };
+    int64_t ncand = cdiv64(N, LU_R) * LU_NB + LU_NB;
+    w.cand0 = (int32_t*)take(ncand * 4);
+    w.cand1 = (int32_t*)take(ncand * 4);
+    int64_t rtiles = cdiv64(N, G_TM) + 1, ctiles = cdiv64(N, G_TN) + 1;
+    int nks = LU_NBO / G_KC;
+    w.Lp = (double*)take(rtiles * nks * G_A_STAGE * 8);
+    w.Up = (double*)take(ctiles * nks * G_B_STAGE * 8);
+    w.bytes = off;
+    return w;
+}
+
+#define LU_LAUNCH_CHECK(ctx)                                  \
+    do {                                                      \
+        cudaError_t e__ = cudaGetLastError();                 \
+        if (e__ != cudaSuccess && !(ctx).err) (ctx).err = (int)e__; \
+    } while (0)
+
+// C[rows r_lo.., cols c_lo..c_hi) -= L[rows, k0..k0+K) * U[k0..k0+K, cols]   (operands already packed)
+static void lu_pack_l(LuCtx& x, int64_t r_lo, int64_t r_hi, int64_t k0, int K);
+static void lu_gemm(LuCtx& x, int64_t r_lo, int64_t r_hi, int64_t c_lo, int64_t c_hi, int64_t k0, int K) {
+    if (r_lo >= r_hi || c_lo >= c_hi || K <= 0) return;
+    // the L operand is packed here, from the current A: pivoting of later panels of the same outer block
+    // permutes rows of earlier L columns, so an image packed at panel time would be stale
+    lu_pack_l(x, r_lo, r_hi, k0, K);
+    GemmArgs g;
+    g.Lp = x.Lp; g.Up = x.Up; g.nks_total = x.nks_total;
+    g.ks0 = (int)((k0 - x.J) / G_KC);
+    g.nks = (K + G_KC - 1) / G_KC;
+    g.C = x.A; g.ldc = x.ld;
+    g.row_base = x.J; g.col_base = 0;
+    g.rt0 = (int)((r_lo - x.J) / G_TM);
+    g.ct0 = (int)(c_lo / G_TN);
+    int rt1 = (int)((r_hi - 1 - x.J) / G_TM), ct1 = (int)((c_hi - 1) / G_TN);
+    g.row_lo = r_lo; g.row_hi = r_hi; g.col_lo = c_lo; g.col_hi = c_hi;
+    dim3 grid(ct1 - g.ct0 + 1, rt1 - g.rt0 + 1);
+    zgemm_sub_kernel<<<grid, G_THREADS, G_SMEM, x.st>>>(g);
+    LU_LAUNCH_CHECK(x);
+}
+static void lu_pack_l(LuCtx& x, int64_t r_lo, int64_t r_hi, int64_t k0, int K) {
+    // rows [r_lo, r_hi) padded up to the tile grid anchored at J (rows >= N are zero filled)
+    if (r_lo >= r_hi) return;
+    int64_t r_end_pad = x.J + cdiv64(r_hi - x.J, G_TM) * G_TM;
+    int Kpad = ((K + G_KC - 1) / G_KC) * G_KC;
+    int64_t tot = (r_end_pad - r_lo) * Kpad;
+    pack_l_kernel<<<(unsigned)cdiv64(tot, 256), 256, 0, x.st>>>(x.A, x.ld, x.N, x.J, r_lo, r_end_pad, k0, K, Kpad, x.Lp,
+                                                               x.nks_total, (int)((k0 - x.J) / G_KC));
+    LU_LAUNCH_CHECK(x);
+}
+static void lu_pack_u(LuCtx& x, int64_t k0, int K, int64_t c_lo, int64_t c_hi) {
+    if (c_lo >= c_hi) return;
+    int64_t c_begin = (c_lo / G_TN) * G_TN, c_end_pad = cdiv64(c_hi, G_TN) * G_TN;
+    int Kpad = ((K + G_KC - 1) / G_KC) * G_KC;
+    int64_t tot = (c_end_pad - c_begin) * Kpad;
+    pack_u_kernel<<<(unsigned)cdiv64(tot, 256), 256, 0, x.st>>>(x.A, x.ld, x.N, k0, K, Kpad, c_begin, c_end_pad, x.Up,
+                                                               x.nks_total, (int)((k0 - x.J) / G_KC));
+    LU_LAUNCH_CHECK(x);
+}
+
+// 32-wide (or narrower) panel at column j: tournament pivoting, swap, diagonal LU, L21
+static void lu_panel(LuCtx& x, int64_t j, int w) {
+    const int64_t M = x.N - j;
+    int64_t nsets = cdiv64(M, LU_R);
+    int cur = 0;
+    lu_select_kernel<<<(unsigned)nsets, LU_R, LU_TILE_SMEM, x.st>>>(x.A, x.ld, j, w, nullptr, 0, j, x.N, x.cand[cur]);
+    LU_LAUNCH_CHECK(x);
+    while (nsets > 1) {
+        int64_t n_in = nsets * LU_NB;
+        int64_t nsets2 = cdiv64(n_in, LU_R);
+        lu_select_kernel<<<(unsigned)nsets2, LU_R, LU_TILE_SMEM, x.st>>>(x.A, x.ld, j, w, x.cand[cur], n_in, 0, 0, x.cand[cur ^ 1]);
+        LU_LAUNCH_CHECK(x);
+        cur ^= 1;
+        nsets = nsets2;
+    }
+    lu_pivots_kernel<<<1, 32, 0, x.st>>>(x.cand[cur], j, w, x.ipiv);
+    LU_LAUNCH_CHECK(x);
+    lu_swap_kernel<<<(unsigned)cdiv64(x.N, 256), 256, 0, x.st>>>(x.A, x.ld, x.N, x.ipiv, j, w);
+    LU_LAUNCH_CHECK(x);
+    if (x.rhs) {
+        lu_swap_kernel<<<(unsigned)cdiv64(x.nrhs, 32), 32, 0, x.st>>>(x.rhs, x.nrhs, x.nrhs, x.ipiv, j, w);
+        LU_LAUNCH_CHECK(x);
+    }
+    lu_diag_kernel<<<1, 256, 0, x.st>>>(x.A, x.ld, j, w, x.info);
+    LU_LAUNCH_CHECK(x);
+    if (j + w < x.N) {
+        lu_l21_kernel<<<(unsigned)cdiv64(x.N - j - w, LU_R), LU_R, LU_TILE_SMEM, x.st>>>(x.A, x.ld, x.N, j, w);
+        LU_LAUNCH_CHECK(x);
+    }
+}
+
+// U[j0..j0+T, cols) = L11^{-1} A[j0..j0+T, cols)   (T multiple of 32 except possibly the tail), packs U
+static void lu_trsm(LuCtx& x, int64_t j0, int T, int64_t c_lo, int64_t c_hi) {
+    if (c_lo >= c_hi || T <= 0) return;
+    if (T <= LU_NB) {
+        lu_trsm32_kernel<<<(unsigned)cdiv64(c_hi - c_lo, 128), 128, 0, x.st>>>(x.A, x.ld, j0, T, x.A, x.ld, c_lo, c_hi);
+        LU_LAUNCH_CHECK(x);
+        lu_pack_u(x, j0, T, c_lo, c_hi);
+        return;
+    }
+    int h = (T > 64) ? 64 : 32;
+    lu_trsm(x, j0, h, c_lo, c_hi);
+    lu_gemm(x, j0 + h, j0 + T, c_lo, c_hi, j0, h);
+    lu_trsm(x, j0 + h, T - h, c_lo, c_hi);
+}
+
+// recursive LU of columns [j0, j0+w) (rows j0..N), w <= 128
+static void lu_rec(LuCtx& x, int64_t j0, int w) {
+    if (w <= LU_NB) {
+        lu_panel(x, j0, w);
+        return;
+    }
+    int h = (w > 64) ? 64 : 32;
+    lu_rec(x, j0, h);
+    lu_trsm(x, j0, h, j0 + h, j0 + w);
+    lu_gemm(x, j0 + h, x.N, j0 + h, j0 + w, j0, h);
+    lu_rec(x, j0 + h, w - h);
+}
+
+static int lu_factor(LuCtx& x) {
+    cudaMemsetAsync(x.info, 0, sizeof(int32_t), x.st);
+    cudaFuncSetAttribute(zgemm_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
+    cudaFuncSetAttribute(lu_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LU_TILE_SMEM);
+    cudaFuncSetAttribute(lu_l21_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LU_TILE_SMEM);
+    for (int64_t J = 0; J < x.N; J += LU_NBO) {
+        int w = (int)((x.N - J < LU_NBO) ? (x.N - J) : LU_NBO);
+        x.J = J;
+        lu_rec(x, J, w);
+        if (x.rhs) {
+            // forward substitution of this block row: y_J = L11^{-1} rhs_J ; rhs_below -= L21 y_J
+            rhs_block_solve_kernel<<<1, 128, 0, x.st>>>(x.A, x.ld, J, w, 0, x.rhs, x.nrhs);
+            LU_LAUNCH_CHECK(x);
+            if (J + w < x.N) {
+                rhs_gemv_sub_kernel<<<(unsigned)cdiv64(x.N - J - w, 8), 256, 0, x.st>>>(x.A, x.ld, J + w, x.N, J, w, x.rhs,
+                                                                                      x.nrhs);
+                LU_LAUNCH_CHECK(x);
+            }
+        }
+        if (J + w < x.N) {
+            lu_trsm(x, J, w, J + w, x.N);
+            lu_gemm(x, J + w, x.N, J + w, x.N, J, w);
+        }
+    }
+    return x.err;
+}
+
+static int lu_backward(LuCtx& x) {
+    // x = U^{-1} y, block rows from the bottom
+    int64_t nblk = cdiv64(x.N, LU_NBO);
+    for (int64_t bi = nblk - 1; bi >= 0; --bi) {
+        int64_t J = bi * LU_NBO;
+        int w = (int)((x.N - J < LU_NBO) ? (x.N - J) : LU_NBO);
+        rhs_block_solve_kernel<<<1, 128, 0, x.st>>>(x.A, x.ld, J, w, 1, x.rhs, x.nrhs);
+        LU_LAUNCH_CHECK(x);
+        if (J > 0) {
+            rhs_gemv_sub_kernel<<<(unsigned)cdiv64(J, 8), 256, 0, x.st>>>(x.A, x.ld, 0, J, J, w, x.rhs, x.nrhs);
+            LU_LAUNCH_CHECK(x);
+        }
+    }
+    return x.err;
+}
+
+extern "C" int64_t bhs_zgesv_workspace(int64_t N, int nrhs) {
+    if (N <= 0 || nrhs < 0) return BHS_ERR_INVALID;
+    return lu_carve(N, nullptr).bytes;
+}
+
+static int lu_setup(LuCtx& x, int64_t N, double* d_A, int64_t ld, double* d_rhs, int nrhs, int32_t* d_ipiv,
+                    int32_t* d_info, void* d_work, void* stream) {
+    if (N <= 0 || !d_A || ld < N || !d_ipiv || !d_info || !d_work) return BHS_ERR_INVALID;
+    if (N > 2000000000LL / LU_NB) return BHS_ERR_UNSUPPORTED;
+    LuWork w = lu_carve(N, d_work);
+    x.A = (cplx*)d_A; x.ld = ld; x.N = N; x.rhs = (cplx*)d_rhs; x.nrhs = nrhs;
+    x.ipiv = d_ipiv; x.info = d_info; x.cand[0] = w.cand0; x.cand[1] = w.cand1;
+    x.Lp = w.Lp; x.Up = w.Up; x.nks_total = LU_NBO / G_KC; x.J = 0;
+    x.st = (cudaStream_t)stream; x.err = 0;
+    return BHS_OK;
+}
+
+extern "C" int bhs_zgetrf(int64_t N, double* d_A, int64_t ld, int32_t* d_ipiv, int32_t* d_info, void* d_work,
+                          void* stream) {
+    LuCtx x;
+    int rc = lu_setup(x, N, d_A, ld, nullptr, 0, d_ipiv, d_info, d_work, stream);
+    if (rc) return rc;
+    return lu_factor(x);
+}
+
+extern "C" int bhs_zgesv(int64_t N, int nrhs, double* d_A, int64_t ld, double* d_rhs, int32_t* d_ipiv,
+                         int32_t* d_info, void* d_work, void* stream) {
+    if (nrhs <= 0 || !d_rhs) return BHS_ERR_INVALID;
+    LuCtx x;
+    int rc = lu_setup(x, N, d_A, ld, d_rhs, nrhs, d_ipiv, d_info, d_work, stream);
+    if (rc) return rc;
+    rc = lu_factor(x);
+    if (rc) return rc;
+    return lu_backward(x);
+}
+
+extern "C" int bhs_zgetrs(int64_t N, int nrhs, const double* d_LU, int64_t ld, const int32_t* d_ipiv, double* d_rhs,
+                          void* d_work, void* stream) {
+    if (N <= 0 || nrhs <= 0 || !d_LU || ld < N || !d_ipiv || !d_rhs) return BHS_ERR_INVALID;
+    (void)d_work;
+    LuCtx x;
+    x.A = (cplx*)d_LU; x.ld = ld; x.N = N; x.rhs = (cplx*)d_rhs; x.nrhs = nrhs;
+    x.st = (cudaStream_t)stream; x.err = 0;
+    rhs_apply_ipiv_kernel<<<1, 32, 0, x.st>>>(d_ipiv, N, x.rhs, nrhs);
+    LU_LAUNCH_CHECK(x);
+    for (int64_t J = 0; J < N; J += LU_NBO) {
+        int w = (int)((N - J < LU_NBO) ? (N - J) : LU_NBO);
+        rhs_block_solve_kernel<<<1, 128, 0, x.st>>>(x.A, ld, J, w, 0, x.rhs, nrhs);
+        LU_LAUNCH_CHECK(x);
+        if (J + w < N) {
+            rhs_gemv_sub_kernel<<<(unsigned)cdiv64(N - J - w, 8), 256, 0, x.st>>>(x.A, ld, J + w, N, J, w, x.rhs, nrhs);
+            LU_LAUNCH_CHECK(x);
+        }
+    }
+    return lu_backward(x);
+}
+
+// ---- stand-alone C -= A*B (row-major operands), for tests and the roofline measurement -------------------
+extern "C" int64_t bhs_zgemm_workspace(int64_t M, int64_t N, int64_t K) {
+    if (M <= 0 || N <= 0 || K <= 0) return BHS_ERR_INVALID;
+    int64_t nks = cdiv64(K, G_KC);
+    return al256((cdiv64(M, G_TM)) * nks * G_A_STAGE * 8) + al256((cdiv64(N, G_TN)) * nks * G_B_STAGE * 8);
+}
+
+extern "C" int bhs_zgemm_sub(int64_t M, int64_t N, int64_t K, const double* d_A, int64_t lda, const double* d_B,
+                             int64_t ldb, double* d_C, int64_t ldc, void* d_work, void* stream) {
+    if (M <= 0 || N <= 0 || K <= 0 || !d_A || !d_B || !d_C || !d_work || lda < K || ldb < N || ldc < N)
+        return BHS_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t nks = cdiv64(K, G_KC);
+    int Kpad = (int)(nks * G_KC);
+    double* Lp = (double*)d_work;
+    double* Up = (double*)((unsigned char*)d_work + al256(cdiv64(M, G_TM) * nks * G_A_STAGE * 8));
+    int64_t r_end_pad = cdiv64(M, G_TM) * G_TM, c_end_pad = cdiv64(N, G_TN) * G_TN;
+    pack_l_kernel<<<(unsigned)cdiv64(r_end_pad * Kpad, 256), 256, 0, st>>>((const cplx*)d_A, lda, M, 0, 0, r_end_pad, 0, (int)K,
+                                                                        Kpad, Lp, (int)nks, 0);
+    BHS_CHECK_LAUNCH();
+    pack_u_kernel<<<(unsigned)cdiv64(c_end_pad * Kpad, 256), 256, 0, st>>>((const cplx*)d_B, ldb, N, 0, (int)K, Kpad, 0,
+                                                                        c_end_pad, Up, (int)nks, 0);
+    BHS_CHECK_LAUNCH();
+    cudaFuncSetAttribute(zgemm_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
+    GemmArgs g;
+    g.Lp = Lp; g.Up = Up; g.nks_total = (int)nks; g.ks0 = 0; g.nks = (int)nks;
+    g.C = (cplx*)d_C; g.ldc = ldc; g.row_base = 0; g.col_base = 0; g.rt0 = 0; g.ct0 = 0;
+    g.row_lo = 0; g.row_hi = M; g.col_lo = 0; g.col_hi = N;
+    dim3 grid((unsigned)cdiv64(N, G_TN), (unsigned)cdiv64(M, G_TM));
+    zgemm_sub_kernel<<<grid, G_THREADS, G_SMEM, st>>>(g);
+    BHS_CHECK_LAUNCH();
+    return BHS_OK;
+}
