@@ -15,8 +15,9 @@ __global__ void __launch_bounds__(128) harmonics_kernel(HarmTables tb, int Lb, c
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t per_warp = harm_smem_bytes_per_warp(tb.d, Lb);
-    double* F = reinterpret_cast<double*>(smem_raw + per_warp * warp);
-    cplx* E = reinterpret_cast<cplx*>(F + (size_t)(tb.d - 2) * Lb * Lb);
+    double* F;
+    cplx* E;
+    harm_smem_carve(smem_raw + per_warp * warp, Lb, F, E);
     const int s = tb.d - 1;
     for (int64_t p = (int64_t)blockIdx.x * warps + warp; p < npts; p += (int64_t)gridDim.x * warps) {
         double x[BHS_MAX_NODES + 2];

@@ -23,6 +23,11 @@ __host__ __device__ inline size_t harm_smem_bytes_per_warp(int d, int Lb) {
     size_t b = (size_t)(d - 2) * Lb * Lb * sizeof(double) + (size_t)Lb * sizeof(cplx);
     return (b + 15) & ~(size_t)15;
 }
+// per-warp scratch layout: E (complex, 16-byte aligned) first, then the node tables F
+__device__ __forceinline__ void harm_smem_carve(unsigned char* base, int Lb, double*& F, cplx*& E) {
+    E = reinterpret_cast<cplx*>(base);
+    F = reinterpret_cast<double*>(base + (size_t)Lb * sizeof(cplx));
+}
 
 __device__ __forceinline__ double powi_d(double b, int e) {
     double r = 1.0;

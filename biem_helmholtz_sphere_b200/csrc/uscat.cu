@@ -262,8 +262,9 @@ __global__ void __launch_bounds__(128) uscat_generic_kernel(UscatArgs a, HarmTab
     const size_t harm_bytes = harm_smem_bytes_per_warp(d, L);
     const size_t rad_bytes = (size_t)2 * (L + 2 + shift) * sizeof(double);
     unsigned char* base = smem_raw + (harm_bytes + rad_bytes) * warp;
-    double* F = reinterpret_cast<double*>(base);
-    cplx* E = reinterpret_cast<cplx*>(F + (size_t)(d - 2) * L * L);
+    double* F;
+    cplx* E;
+    harm_smem_carve(base, L, F, E);
     double* Hr = reinterpret_cast<double*>(base + harm_bytes);
     double* Hi = Hr + (L + 2 + shift);
     const bool far = a.flags & BHS_FLAG_FAR_FIELD, inner = a.flags & BHS_FLAG_INNER, per_ball = a.flags & BHS_FLAG_PER_BALL;
