@@ -1,0 +1,305 @@
+"""GPU parity tests through the public (reference-shaped) API: biem(...) -> BIEMResultCalculator.uscat(...).
+
+Checked against (a) the reference's golden vectors (tests/golden/*.csv, README known answer) and (b) the CPU
+oracle on the same inputs.  Tolerance: 1e-10 relative (BASELINE.json north_star) unless a test says otherwise.
+"""
+import warnings
+
+import numpy as np
+import pytest
+
+from golden_util import find, load
+from oracle import biem_oracle as bo
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def bhs():
+    import torch
+
+    assert torch.cuda.is_available()
+    import biem_helmholtz_sphere_b200 as m
+
+    return m
+
+
+def rel(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+
+
+def run_ref_style(bhs, btype, n_end, k=1.0, half=0, uin_k=1.0):
+    """The reference CLI's call (cli.py:236-257): plane wave built with uin_k (quirk: always 1), solve at k."""
+    c = bhs.create_from_branching_types(btype)
+    d = c.c_ndim
+    xp = np
+    uin = bhs.plane_wave(k=xp.asarray(uin_k), direction=xp.asarray((1.0,) + (0.0,) * (d - 1)))[0]
+    cen = bo.grid_centers(half, d)
+    calc = bhs.biem(c, uin=uin, k=xp.asarray(k), n_end=n_end, eta=xp.asarray(1.0), centers=xp.asarray(cen),
+                    radii=xp.asarray((1.0,) * len(cen)), kind="outer")
+    assert not np.any(np.isnan(calc.density))
+    return calc, complex(calc.uscat(xp.asarray((0.0,) * d)))
+
+
+def test_readme_example(bhs):
+    xp = np
+    c = bhs.create_from_branching_types("ba")
+    uin, uin_grad = bhs.plane_wave(k=xp.asarray(1.0), direction=xp.asarray((1.0, 0.0, 0.0)))
+    calc = bhs.biem(c, uin=uin, uin_grad=uin_grad, k=xp.asarray(1.0), n_end=6, eta=xp.asarray(1.0),
+                    centers=xp.asarray(((0.0, 2.0, 0.0), (0.0, -2.0, 0.0))), radii=xp.asarray((1.0, 1.0)), kind="outer")
+    assert isinstance(calc, bhs.BIEMResultCalculator)
+    v = calc.uscat(xp.asarray((0.0, 0.0, 0.0)))
+    assert complex(xp.round(v, 6)) == (-0.741333 - 0.669657j)
+    assert abs(complex(v) - (-0.74133301331334 - 0.6696574197988229j)) < TOL
+    # record layout of the reference: centers transposed [d, B], density [B, H], matrix [B, H, B, H]
+    assert calc.centers.shape == (3, 2) and calc.density.shape == (2, 36) and calc.matrix.shape == (2, 36, 2, 36)
+    assert calc.density.dtype == np.complex128 and isinstance(calc.density, np.ndarray)
+
+
+@pytest.mark.parametrize("n_end", [1, 2, 4, 6, 9, 12, 16, 24, 32])
+def test_golden_3d_k1(bhs, n_end):
+    row = find([r for r in load("accuracy_k_ba.csv") if r["branching_types"] == "ba"], n_end=n_end, k=1.0)[0]
+    _, v = run_ref_style(bhs, "ba", n_end)
+    assert abs(v - row["uscat"]) <= TOL * abs(row["uscat"])
+
+
+@pytest.mark.parametrize("k", [2.0 ** 0.5, 2.0, 4.0, 8.0, 16.0])
+def test_golden_3d_k_sweep(bhs, k):
+    row = find([r for r in load("accuracy_k_ba.csv") if r["branching_types"] == "ba"], n_end=16, k=k)[0]
+    _, v = run_ref_style(bhs, "ba", 16, k=k)
+    assert abs(v - row["uscat"]) <= TOL * max(1.0, abs(row["uscat"]))
+
+
+@pytest.mark.parametrize("n_end", [1, 3, 8, 16, 32, 38])
+def test_golden_2d_k1(bhs, n_end):
+    row = find(load("accuracy_k_a.csv"), n_end=n_end, k=1.0)[0]
+    _, v = run_ref_style(bhs, "a", n_end)
+    assert abs(v - row["uscat"]) <= TOL * abs(row["uscat"])
+
+
+@pytest.mark.parametrize("k,n_end", [(2.0, 16), (4.0, 8), (8.0, 32), (64.0, 128)])
+def test_golden_2d_k_sweep(bhs, k, n_end):
+    row = find(load("accuracy_k_a.csv"), n_end=n_end, k=k)[0]
+    _, v = run_ref_style(bhs, "a", n_end, k=k)
+    assert abs(v - row["uscat"]) <= TOL * max(1.0, abs(row["uscat"]))
+
+
+@pytest.mark.parametrize("half,n_end", [(1, 32), (2, 32), (4, 32), (8, 16)])
+def test_golden_2d_grids(bhs, half, n_end):
+    row = find(load("accuracy_n_balls_a.csv"), n_end=n_end, n_balls=(2 * half) ** 2)[0]
+    _, v = run_ref_style(bhs, "a", n_end, half=half)
+    assert abs(v - row["uscat"]) <= TOL * abs(row["uscat"])
+
+
+TRIPLET_TOL = {1: TOL, 2: TOL, 3: TOL, 4: TOL, 5: TOL, 6: 5e-10, 7: 1e-9, 8: 2e-9, 9: 1e-7}
+
+
+@pytest.mark.parametrize("btype", ["a", "ba", "bba"])
+def test_golden_jascome(bhs, btype):
+    """Forced-`triplet` rows carry the reference's own quadrature noise for n_end >= 6."""
+    for r in [r for r in load("jascome_output.csv") if r["branching_types"] == btype]:
+        _, v = run_ref_style(bhs, btype, r["n_end"])
+        assert abs(v - r["uscat"]) <= TRIPLET_TOL[r["n_end"]] * abs(r["uscat"]), (btype, r["n_end"])
+
+
+# ---- oracle parity on the BASELINE configs ------------------------------------------------------------
+def oracle_case(btype, cen, radii, k, n_end, eta=1.0, alpha=1.0, beta=0.0, direction=None, grad=False):
+    d = len(btype) + 1
+    direction = np.array([1.0] + [0.0] * (d - 1)) if direction is None else direction
+    uin, uin_grad = bo.plane_wave(k=k, direction=direction)
+    return bo.biem(btype, uin=uin, uin_grad=uin_grad if grad else None, k=k, n_end=n_end, eta=eta, centers=cen,
+                   radii=radii, alpha=alpha, beta=beta)
+
+
+def probe_points(d, n, lim, seed=0):
+    rng = np.random.default_rng(seed)
+    return rng.uniform(-lim, lim, size=(d, n))
+
+
+@pytest.mark.parametrize("half", [0, 1, 2, 4])
+def test_c2_2d_sweep(bhs, half):
+    """C2: 2-D 'a', n_end = 32, spacing-4 grids, k = 1..10 as ONE batched call vs scalar oracle calls."""
+    d, n_end = 2, 32
+    cen = bo.grid_centers(half, d)
+    B = len(cen)
+    ks = np.arange(1.0, 11.0) if B <= 16 else np.array([1.0, 4.0, 10.0])
+    c = bhs.create_from_branching_types("a")
+    uin, _ = bhs.plane_wave(k=ks, direction=np.array([[1.0], [0.0]]))
+    calc = bhs.biem(c, uin=uin, k=ks, n_end=n_end, eta=np.ones_like(ks), centers=cen[None], radii=np.ones((1, B)),
+                    keep_matrix=False)
+    assert calc.matrix is None and calc.density.shape == (len(ks), B, 2 * n_end - 1)
+    x = probe_points(d, 64, 4.0 * max(half, 1) + 3.0)
+    u = calc.uscat(x)  # [64, K]
+    for i, k in enumerate(ks):
+        ref = oracle_case("a", cen, np.ones(B), float(k), n_end)
+        assert rel(calc.density[i], ref.density) < TOL
+        ur = ref.uscat(x)
+        ok = ~np.isnan(ur)
+        assert np.array_equal(np.isnan(u[:, i]), ~ok)
+        assert rel(u[ok, i], ur[ok]) < TOL
+
+
+@pytest.mark.parametrize("k", [0.5, 3.7, 8.0])
+def test_c3_3d_16_spheres(bhs, k):
+    """C3: 3-D 'ba', 4x4 grid of 16 unit spheres, n_end = 16 (N = 4096): density, matrix and probes."""
+    d, n_end = 3, 16
+    cen = bo.grid_centers(2, d)
+    c = bhs.create_from_branching_types("ba")
+    uin, _ = bhs.plane_wave(k=np.asarray(k), direction=np.array([1.0, 0.0, 0.0]))
+    calc = bhs.biem(c, uin=uin, k=np.asarray(k), n_end=n_end, eta=np.asarray(1.0), centers=cen, radii=np.ones(16))
+    ref = oracle_case("ba", cen, np.ones(16), k, n_end)
+    N = 16 * 256
+    Ag, Ar = calc.matrix.reshape(N, N), ref.matrix.reshape(N, N)
+    assert rel(Ag, Ar) < 1e-12
+    assert rel(calc.density, ref.density) < TOL
+    x = np.concatenate([np.zeros((d, 1)), probe_points(d, 64, 9.0)], axis=1)
+    u, ur = calc.uscat(x), ref.uscat(x)
+    ok = ~np.isnan(ur)
+    assert np.array_equal(np.isnan(u), ~ok) and rel(u[ok], ur[ok]) < TOL
+
+
+@pytest.mark.parametrize("B", [2, 8])
+def test_c4_4d(bhs, B):
+    """C4: 4-D 'bba', n_end = 10 (H = 385); B = 2 and the 2x2x2 grid, k in {0.5, 1, 2, 4} batched."""
+    d, n_end = 4, 10
+    if B == 2:
+        cen = bo.grid_centers(0, d)
+    else:
+        g = np.array([-2.0, 2.0])
+        cen = np.stack(np.meshgrid(g, g, g, indexing="ij"), axis=-1).reshape(-1, 3)
+        cen = np.concatenate([cen, np.zeros((8, 1))], axis=1)
+    ks = np.array([0.5, 1.0, 2.0, 4.0])
+    c = bhs.create_from_branching_types("bba")
+    direction = np.zeros((d, 1))
+    direction[0] = 1.0
+    uin, _ = bhs.plane_wave(k=ks, direction=direction)
+    calc = bhs.biem(c, uin=uin, k=ks, n_end=n_end, eta=np.ones(4), centers=cen[None], radii=np.ones((1, B)),
+                    keep_matrix=False)
+    x = np.concatenate([np.zeros((d, 1)), probe_points(d, 32, 5.0)], axis=1)
+    u = calc.uscat(x)
+    for i, k in enumerate(ks):
+        ref = oracle_case("bba", cen, np.ones(B), float(k), n_end)
+        assert rel(calc.density[i], ref.density) < TOL
+        ur = ref.uscat(x)
+        ok = ~np.isnan(ur)
+        assert rel(u[ok, i], ur[ok]) < TOL
+
+
+# ---- API behaviour -------------------------------------------------------------------------------------
+def test_batched_k_equals_scalar_loop_and_torch_inputs(bhs):
+    import torch
+
+    d, n_end = 3, 8
+    cen = np.array([[0.0, 2.0, 0.3], [0.5, -2.0, 0.0], [4.0, 0.0, -1.0]])
+    rad = np.array([1.0, 0.8, 1.2])
+    ks = np.array([0.7, 1.3, 2.9, 5.1, 6.0])
+    c = bhs.create_from_branching_types("ba")
+    dirn = np.array([0.3, -0.5, 0.8])
+    uin, uin_grad = bhs.plane_wave(k=ks, direction=dirn[:, None])
+    batched = bhs.biem(c, uin=uin, uin_grad=uin_grad, k=ks, n_end=n_end, eta=np.full(5, 0.7), centers=cen[None],
+                       radii=rad[None], alpha=1.0, beta=0.3 + 0.1j)
+    x = probe_points(d, 50, 6.0)
+    ub = batched.uscat(x)
+    for i, k in enumerate(ks):
+        ui, ugi = bhs.plane_wave(k=torch.tensor(k, dtype=torch.float64), direction=torch.tensor(dirn))
+        one = bhs.biem(c, uin=ui, uin_grad=ugi, k=torch.tensor(k, dtype=torch.float64), n_end=n_end,
+                       eta=torch.tensor(0.7, dtype=torch.float64), centers=torch.tensor(cen), radii=torch.tensor(rad),
+                       alpha=1.0, beta=0.3 + 0.1j)
+        assert isinstance(one.density, torch.Tensor) and one.density.device.type == "cpu"
+        assert rel(batched.density[i], one.density.numpy()) < 1e-12
+        assert rel(batched.matrix[i], one.matrix.numpy()) < 1e-12
+        u1 = one.uscat(torch.tensor(x)).numpy()
+        ok = ~np.isnan(u1)
+        assert rel(ub[ok, i], u1[ok]) < 1e-12
+        ref = bo.biem("ba", uin=bo.plane_wave(k=k, direction=dirn)[0], uin_grad=bo.plane_wave(k=k, direction=dirn)[1],
+                      k=k, n_end=n_end, eta=0.7, centers=cen, radii=rad, alpha=1.0, beta=0.3 + 0.1j)
+        assert rel(one.density.numpy(), ref.density) < TOL
+
+
+def test_generic_callable_matches_fused_plane_wave(bhs):
+    d, n_end = 3, 7
+    cen = np.array([[0.0, 2.0, 0.0], [0.0, -2.0, 0.0]])
+    c = bhs.create_from_branching_types("ba")
+    k = np.asarray(1.7)
+    uin, uin_grad = bhs.plane_wave(k=k, direction=np.array([1.0, 1.0, 0.0]))
+    fused = bhs.biem(c, uin=uin, uin_grad=uin_grad, k=k, n_end=n_end, centers=cen, radii=np.ones(2), alpha=0.5, beta=1.0)
+    generic = bhs.biem(c, uin=lambda x: uin(x), uin_grad=lambda x: uin_grad(x), k=k, n_end=n_end, centers=cen,
+                       radii=np.ones(2), alpha=0.5, beta=1.0)
+    assert rel(generic.density, fused.density) < 1e-13
+    # stored uin wrapper appends the batch axes (none here) and evaluates the user's callable
+    assert np.allclose(fused.uin(np.zeros((3, 4))), 1.0)
+
+
+def test_single_sphere_shortcut_and_force_matrix(bhs):
+    for btype in ["a", "ba", "bba"]:
+        c = bhs.create_from_branching_types(btype)
+        d = c.c_ndim
+        k = np.asarray(1.4)
+        uin, uin_grad = bhs.plane_wave(k=k, direction=np.eye(d)[0])
+        kw = dict(uin=uin, uin_grad=uin_grad, k=k, n_end=8, eta=np.asarray(1.0), centers=np.zeros((1, d)) + 0.25,
+                  radii=np.array([0.9]), alpha=1.0, beta=0.2j)
+        short = bhs.biem(c, **kw)
+        full = bhs.biem(c, force_matrix=True, **kw)
+        assert short.matrix is None and full.matrix is not None
+        assert rel(short.density, full.density) < 1e-12
+        ref = bo.biem(btype, uin=bo.plane_wave(k=1.4, direction=np.eye(d)[0])[0],
+                      uin_grad=bo.plane_wave(k=1.4, direction=np.eye(d)[0])[1], k=1.4, n_end=8, eta=1.0,
+                      centers=np.zeros((1, d)) + 0.25, radii=np.array([0.9]), alpha=1.0, beta=0.2j)
+        assert rel(short.density, ref.density) < TOL
+
+
+def test_matrix_only_and_errors(bhs):
+    c = bhs.create_from_branching_types("ba")
+    cen = np.array([[0.0, 2.0, 0.0], [0.0, -2.0, 0.0]])
+    calc = bhs.biem(c, k=np.asarray(1.0), n_end=4, centers=cen, radii=np.ones(2))
+    assert calc.density is None and calc.matrix.shape == (2, 16, 2, 16)
+    with pytest.raises(ValueError):
+        calc.uscat(np.zeros(3))
+    with pytest.raises(ValueError):
+        bhs.biem(c, k=np.asarray(1.0), n_end=4, centers=np.zeros((2, 2)), radii=np.ones(2))
+    with pytest.raises(ValueError):
+        bhs.biem(c, k=np.asarray([1.0, 2.0]), n_end=4, centers=cen, radii=np.ones(2))  # rank mismatch
+    with pytest.raises(ValueError):
+        bhs.biem(c, k=np.asarray(1.0), n_end=4, centers=cen, radii=np.ones(2), uin_grad=lambda x: x)  # alpha != 0, no uin
+    with pytest.raises(ValueError):
+        bhs.plane_wave(k=np.asarray(1.0), direction=np.ones((3, 2)))
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        bhs.biem(c, k=np.asarray(1.0), n_end=3, centers=cen, radii=np.ones(2), eta=np.asarray(0.0))
+        assert any("eigenvalue" in str(x.message) for x in w)
+    with pytest.raises(NotImplementedError):
+        bhs.create_from_branching_types("caa")
+
+
+def test_per_ball_far_field_inner_point_source(bhs):
+    d, n_end = 3, 10
+    cen = np.array([[0.0, 2.0, 0.0], [0.0, -2.0, 0.0], [3.0, 0.0, 1.0]])
+    rad = np.array([1.0, 0.7, 0.5])
+    c = bhs.create_from_branching_types("ba")
+    k = np.asarray(2.2)
+    src = np.array([-5.0, 0.5, 0.2])
+    uin, uin_grad = bhs.plane_wave(k=k, direction=np.array([1.0, 0.0, 0.0]))
+    calc = bhs.biem(c, uin=uin, k=k, n_end=n_end, centers=cen, radii=rad)
+    ref = oracle_case("ba", cen, rad, 2.2, n_end)
+    x = probe_points(d, 40, 5.0).reshape(d, 8, 5)
+    pb = calc.uscat(x, per_ball=True)
+    assert pb.shape == (8, 5, 3)
+    want = ref.uscat(x, per_ball=True)
+    ok = ~np.isnan(want)
+    assert rel(pb[ok], want[ok]) < TOL
+    xhat = x / np.linalg.norm(x, axis=0, keepdims=True)
+    ff = calc.uscat(xhat, far_field=True, per_ball=True)
+    assert rel(ff, ref.uscat(xhat, far_field=True, per_ball=True)) < TOL
+    # point source incident field (values from the bhs_bessel kernel) against the oracle's scipy version
+    pu, pg = bhs.point_source(k=k, source=src, n=0)
+    ou, og = bo.point_source(k=2.2, source=src, n=0)
+    calc_ps = bhs.biem(c, uin=pu, uin_grad=pg, k=k, n_end=n_end, centers=cen, radii=rad, alpha=1.0, beta=0.5)
+    ref_ps = bo.biem("ba", uin=ou, uin_grad=og, k=2.2, n_end=n_end, centers=cen, radii=rad, alpha=1.0, beta=0.5)
+    assert rel(calc_ps.density, ref_ps.density) < TOL
+    # interior problem NaN mask
+    calc_in = bhs.biem(c, uin=uin, k=k, n_end=n_end, centers=cen[:1], radii=rad[:1], kind="inner")
+    xi = cen[0][:, None] + probe_points(d, 30, 0.9, seed=3)
+    ui = calc_in.uscat(xi)
+    assert np.array_equal(np.isnan(ui), np.linalg.norm(xi - cen[0][:, None], axis=0) > rad[0])
