@@ -607,6 +607,7 @@ def biem(
     cen_store = ns.out(torch.movedim(cen, -1, 0))  # [v, ..., B]  (_biem.py:588)
     dev_state = {
         "bt": bt, "batch_shape": batch_shape, "K": K, "B": B, "ks": ks, "etas": ets,
+        "ks_host": ks.tolist(), "etas_host": ets.tolist(),
         "cen": cen, "rad": rad, "density": density_t, "geom_shared": shared_geom,
     }
     return BIEMResultCalculator(
@@ -662,9 +663,11 @@ def biem_u(res: Any, x: Array, /, far_field: bool = False, per_ball: bool = Fals
         xshape = tuple(xs.shape[1 : xs.dim() - nb])
         xb = torch.broadcast_to(xs, (d,) + xshape + batch_shape).reshape(d, -1, K)
         per_sys = [xb[:, :, i].contiguous() for i in range(K)]
+    ks_host = st.get("ks_host") or st["ks"].tolist()
+    etas_host = st.get("etas_host") or st["etas"].tolist()
     outs = []
     for i in range(K):
-        o = _ops.uscat(d, n_end, cen_k[i].contiguous(), rad_k[i].contiguous(), float(st["ks"][i]), float(st["etas"][i]),
+        o = _ops.uscat(d, n_end, cen_k[i].contiguous(), rad_k[i].contiguous(), ks_host[i], etas_host[i],
                        dens[i].contiguous(), per_sys[i], far_field=far_field, per_ball=per_ball,
                        inner=(res.kind == "inner"))
         outs.append(o)

@@ -43,9 +43,13 @@ SIGNATURES = {
     "bhs_uscat_workspace": (i64, [vp, i32]),
     "bhs_uscat": (i32, [vp, i32, vp, vp, f64, f64, vp, vp, i64, i32, vp, vp, vp]),
     "bhs_fp64_peak": (i32, [i32, i32, C.POINTER(f64)]),
+    "bhs_launch_count": (i64, [i32]),
+    "bhs_profile": (i32, [i32]),
+    "bhs_profile_read": (i32, [i32, C.POINTER(f64), C.POINTER(f64), C.POINTER(i64)]),
 }
 
 KIND_J, KIND_Y, KIND_H1 = 0, 1, 2
+PROF_CATEGORIES = ("lu_gemm", "lu_panel", "lu_trsm", "lu_pack", "lu_rhs", "asm_main", "asm_pre", "uscat", "rhs_expand")
 FLAG_PER_BALL, FLAG_FAR_FIELD, FLAG_INNER = 1, 2, 4
 
 

@@ -184,3 +184,23 @@ def fp64_peak(shape: int, iters: int = 4096) -> float:
     v = C.c_double()
     check(load().bhs_fp64_peak(shape, iters, C.byref(v)), "bhs_fp64_peak")
     return v.value
+
+
+def launch_count(reset: bool = False) -> int:
+    """Kernel launches issued by libbhs since the last reset (bhs_launch_count)."""
+    return int(load().bhs_launch_count(int(reset)))
+
+
+def profile(enable: bool) -> None:
+    """Enable / disable (and clear) the per-category CUDA-event profiler (bhs_profile)."""
+    check(load().bhs_profile(int(enable)), "bhs_profile")
+
+
+def profile_read() -> dict:
+    """{category: {"ms", "work", "count"}} accumulated since profile(True)   (bhs_profile_read)."""
+    out = {}
+    for i, name in enumerate(_lib.PROF_CATEGORIES):
+        ms, wk, n = C.c_double(), C.c_double(), C.c_int64()
+        check(load().bhs_profile_read(i, C.byref(ms), C.byref(wk), C.byref(n)), "bhs_profile_read")
+        out[name] = {"ms": ms.value, "work": wk.value, "count": n.value}
+    return out

@@ -11,6 +11,7 @@
 // against the resident tile (2 DFMA per term).  Output rows are written as 1 KB contiguous segments.
 // The i^{n}, (-i)^{n'} phase split and the radial row/column factors are folded into two small vectors.
 #include "harmonics.cuh"
+#include "prof.h"
 #include "radial.cuh"
 #include "special.cuh"
 
@@ -251,6 +252,7 @@ extern "C" int bhs_assemble(const bhs_plan_t* plan, int B, int nsys, const doubl
     if (ld < N) return BHS_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     AsmWork w = carve(plan, B, nsys, d_work);
+    bhs_prof_begin(BHS_PROF_ASM_PRE, st);
     int rc = run_factors(plan, B, nsys, d_radii, d_k, d_eta, d_alpha, d_beta, w, false, st);
     if (rc) return rc;
     const int64_t np = (int64_t)B * B;
@@ -297,7 +299,10 @@ extern "C" int bhs_assemble(const bhs_plan_t* plan, int B, int nsys, const doubl
     a.pairs_per_cta = (int)ppc;
     if (chunks > 65535 || nsys > 65535) return BHS_ERR_UNSUPPORTED;
     dim3 grid((unsigned)ntiles, (unsigned)chunks, (unsigned)nsys);
+    bhs_prof_end(BHS_PROF_ASM_PRE, 0.0, st);
+    bhs_prof_begin(BHS_PROF_ASM_MAIN, st);
     assemble_kernel<<<grid, ASM_THREADS, smem, st>>>(a);
+    bhs_prof_end(BHS_PROF_ASM_MAIN, 16.0 * (double)N * (double)N * nsys, st);
     BHS_CHECK_LAUNCH();
     return BHS_OK;
 }
@@ -372,10 +377,12 @@ extern "C" int bhs_rhs_expand(const bhs_plan_t* plan, int B, int nsys, const dou
     if (smem > 200 * 1024) return BHS_ERR_UNSUPPORTED;
     cudaFuncSetAttribute(rhs_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((plan->H + 127) / 128, B, nsys);
+    bhs_prof_begin(BHS_PROF_RHS_EXPAND, (cudaStream_t)stream);
     rhs_expand_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(plan->d, B, plan->H, plan->Q, (const cplx*)d_g,
                                                                  d_centers, d_radii, d_k_in, d_dir,
                                                                  (const cplx*)d_alpha, (const cplx*)d_beta,
                                                                  plan->d_qdirs, plan->d_WY, (cplx*)d_out);
+    bhs_prof_end(BHS_PROF_RHS_EXPAND, 0.0, (cudaStream_t)stream);
     BHS_CHECK_LAUNCH();
     return BHS_OK;
 }

@@ -129,13 +129,3 @@ extern "C" int bhs_fp64_peak(int shape, int iters, double* tflops_out) {
     *tflops_out = best;
     return BHS_OK;
 }
-
-extern "C" int bhs_version(void) { return 100; }
-extern "C" int bhs_device_sm_count(int* out) {
-    if (!out) return BHS_ERR_INVALID;
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaDeviceGetAttribute(out, cudaDevAttrMultiProcessorCount, dev);
-    return e == cudaSuccess ? BHS_OK : (int)e;
-}

@@ -6,8 +6,13 @@
 
 #include "../../include/bhs.h"
 
+// every kernel launch of the library is followed by one of the *_CHECK macros, which also count it
+// (bhs_launch_count: evidence for bench.py's gpu_launches)
+extern unsigned long long g_bhs_launches;
+#define BHS_COUNT_LAUNCH() __sync_fetch_and_add(&g_bhs_launches, 1ULL)
 #define BHS_CHECK_LAUNCH()                         \
     do {                                           \
+        BHS_COUNT_LAUNCH();                        \
         cudaError_t e__ = cudaGetLastError();      \
         if (e__ != cudaSuccess) return (int)e__;   \
     } while (0)

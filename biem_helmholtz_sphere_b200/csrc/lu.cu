@@ -11,6 +11,7 @@
 //   triangular-solve kernels into the exact shared-memory image (padded, conflict-free) so that every
 //   pipeline stage is two 1-D TMA bulk copies (cp.async.bulk + mbarrier), 3 stages deep.
 #include "common.cuh"
+#include "prof.h"
 
 #define LU_NB 32     // panel width
 #define LU_NBO 128   // outer block width
@@ -495,6 +496,7 @@ static LuWork lu_carve(int64_t N, void* base) {
 
 #define LU_LAUNCH_CHECK(ctx)                                  \
     do {                                                      \
+        BHS_COUNT_LAUNCH();                                   \
         cudaError_t e__ = cudaGetLastError();                 \
         if (e__ != cudaSuccess && !(ctx).err) (ctx).err = (int)e__; \
     } while (0)
@@ -517,7 +519,9 @@ static void lu_gemm(LuCtx& x, int64_t r_lo, int64_t r_hi, int64_t c_lo, int64_t 
     int rt1 = (int)((r_hi - 1 - x.J) / G_TM), ct1 = (int)((c_hi - 1) / G_TN);
     g.row_lo = r_lo; g.row_hi = r_hi; g.col_lo = c_lo; g.col_hi = c_hi;
     dim3 grid(ct1 - g.ct0 + 1, rt1 - g.rt0 + 1);
+    bhs_prof_begin(BHS_PROF_LU_GEMM, x.st);
     zgemm_sub_kernel<<<grid, G_THREADS, G_SMEM, x.st>>>(g);
+    bhs_prof_end(BHS_PROF_LU_GEMM, 8.0 * (double)(r_hi - r_lo) * (double)(c_hi - c_lo) * (double)K, x.st);
     LU_LAUNCH_CHECK(x);
 }
 static void lu_pack_l(LuCtx& x, int64_t r_lo, int64_t r_hi, int64_t k0, int K) {
@@ -526,8 +530,10 @@ static void lu_pack_l(LuCtx& x, int64_t r_lo, int64_t r_hi, int64_t k0, int K) {
     int64_t r_end_pad = x.J + cdiv64(r_hi - x.J, G_TM) * G_TM;
     int Kpad = ((K + G_KC - 1) / G_KC) * G_KC;
     int64_t tot = (r_end_pad - r_lo) * Kpad;
+    bhs_prof_begin(BHS_PROF_LU_PACK, x.st);
     pack_l_kernel<<<(unsigned)cdiv64(tot, 256), 256, 0, x.st>>>(x.A, x.ld, x.N, x.J, r_lo, r_end_pad, k0, K, Kpad, x.Lp,
                                                                x.nks_total, (int)((k0 - x.J) / G_KC));
+    bhs_prof_end(BHS_PROF_LU_PACK, 0.0, x.st);
     LU_LAUNCH_CHECK(x);
 }
 static void lu_pack_u(LuCtx& x, int64_t k0, int K, int64_t c_lo, int64_t c_hi) {
@@ -535,8 +541,10 @@ static void lu_pack_u(LuCtx& x, int64_t k0, int K, int64_t c_lo, int64_t c_hi) {
     int64_t c_begin = (c_lo / G_TN) * G_TN, c_end_pad = cdiv64(c_hi, G_TN) * G_TN;
     int Kpad = ((K + G_KC - 1) / G_KC) * G_KC;
     int64_t tot = (c_end_pad - c_begin) * Kpad;
+    bhs_prof_begin(BHS_PROF_LU_PACK, x.st);
     pack_u_kernel<<<(unsigned)cdiv64(tot, 256), 256, 0, x.st>>>(x.A, x.ld, x.N, k0, K, Kpad, c_begin, c_end_pad, x.Up,
                                                                x.nks_total, (int)((k0 - x.J) / G_KC));
+    bhs_prof_end(BHS_PROF_LU_PACK, 0.0, x.st);
     LU_LAUNCH_CHECK(x);
 }
 
@@ -545,6 +553,7 @@ static void lu_panel(LuCtx& x, int64_t j, int w) {
     const int64_t M = x.N - j;
     int64_t nsets = cdiv64(M, LU_R);
     int cur = 0;
+    bhs_prof_begin(BHS_PROF_LU_PANEL, x.st);
     lu_select_kernel<<<(unsigned)nsets, LU_R, LU_TILE_SMEM, x.st>>>(x.A, x.ld, j, w, nullptr, 0, j, x.N, x.cand[cur]);
     LU_LAUNCH_CHECK(x);
     while (nsets > 1) {
@@ -569,13 +578,16 @@ static void lu_panel(LuCtx& x, int64_t j, int w) {
         lu_l21_kernel<<<(unsigned)cdiv64(x.N - j - w, LU_R), LU_R, LU_TILE_SMEM, x.st>>>(x.A, x.ld, x.N, j, w);
         LU_LAUNCH_CHECK(x);
     }
+    bhs_prof_end(BHS_PROF_LU_PANEL, 0.0, x.st);
 }
 
 // U[j0..j0+T, cols) = L11^{-1} A[j0..j0+T, cols)   (T multiple of 32 except possibly the tail), packs U
 static void lu_trsm(LuCtx& x, int64_t j0, int T, int64_t c_lo, int64_t c_hi) {
     if (c_lo >= c_hi || T <= 0) return;
     if (T <= LU_NB) {
+        bhs_prof_begin(BHS_PROF_LU_TRSM, x.st);
         lu_trsm32_kernel<<<(unsigned)cdiv64(c_hi - c_lo, 128), 128, 0, x.st>>>(x.A, x.ld, j0, T, x.A, x.ld, c_lo, c_hi);
+        bhs_prof_end(BHS_PROF_LU_TRSM, 0.0, x.st);
         LU_LAUNCH_CHECK(x);
         lu_pack_u(x, j0, T, c_lo, c_hi);
         return;
@@ -610,6 +622,7 @@ static int lu_factor(LuCtx& x) {
         lu_rec(x, J, w);
         if (x.rhs) {
             // forward substitution of this block row: y_J = L11^{-1} rhs_J ; rhs_below -= L21 y_J
+            bhs_prof_begin(BHS_PROF_LU_RHS, x.st);
             rhs_block_solve_kernel<<<1, 128, 0, x.st>>>(x.A, x.ld, J, w, 0, x.rhs, x.nrhs);
             LU_LAUNCH_CHECK(x);
             if (J + w < x.N) {
@@ -617,6 +630,7 @@ static int lu_factor(LuCtx& x) {
                                                                                       x.nrhs);
                 LU_LAUNCH_CHECK(x);
             }
+            bhs_prof_end(BHS_PROF_LU_RHS, 0.0, x.st);
         }
         if (J + w < x.N) {
             lu_trsm(x, J, w, J + w, x.N);
@@ -629,6 +643,7 @@ static int lu_factor(LuCtx& x) {
 static int lu_backward(LuCtx& x) {
     // x = U^{-1} y, block rows from the bottom
     int64_t nblk = cdiv64(x.N, LU_NBO);
+    bhs_prof_begin(BHS_PROF_LU_RHS, x.st);
     for (int64_t bi = nblk - 1; bi >= 0; --bi) {
         int64_t J = bi * LU_NBO;
         int w = (int)((x.N - J < LU_NBO) ? (x.N - J) : LU_NBO);
@@ -639,6 +654,7 @@ static int lu_backward(LuCtx& x) {
             LU_LAUNCH_CHECK(x);
         }
     }
+    bhs_prof_end(BHS_PROF_LU_RHS, 0.0, x.st);
     return x.err;
 }
 

@@ -11,6 +11,7 @@
 // Generic path (uscat_generic_kernel): one warp per point, node tables in shared memory -- any chain
 // type / any n_end (2-D, 4-D, 3-D beyond the register-resident limit).
 #include "harmonics.cuh"
+#include "prof.h"
 #include "radial.cuh"
 #include "special.cuh"
 
@@ -361,7 +362,9 @@ static int launch_uscat3d(const UscatArgs& a, cudaStream_t st) {
     size_t smem = (size_t)(2 * US3D_CB * (4 + 4 * npair) + npair) * sizeof(double);
     cudaFuncSetAttribute(uscat3d_kernel<LMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int64_t blocks = (a.P + US3D_THREADS - 1) / US3D_THREADS;
+    bhs_prof_begin(BHS_PROF_USCAT, st);
     uscat3d_kernel<LMAX><<<(unsigned)blocks, US3D_THREADS, smem, st>>>(a);
+    bhs_prof_end(BHS_PROF_USCAT, 8.0 * (double)a.P * a.B * a.H, st);
     BHS_CHECK_LAUNCH();
     return BHS_OK;
 }
@@ -411,7 +414,9 @@ extern "C" int bhs_uscat(const bhs_plan_t* plan, int B, const double* d_centers,
     cudaFuncSetAttribute(uscat_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int64_t blocks = (P + warps - 1) / warps;
     if (blocks > 148 * 16) blocks = 148 * 16;
+    bhs_prof_begin(BHS_PROF_USCAT, st);
     uscat_generic_kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(a, harm_tables_of(plan));
+    bhs_prof_end(BHS_PROF_USCAT, 8.0 * (double)a.P * a.B * a.H, st);
     BHS_CHECK_LAUNCH();
     return BHS_OK;
 }

@@ -135,7 +135,27 @@ int bhs_uscat(const bhs_plan_t *plan, int B, const double *d_centers, const doub
               double k, double eta, const double *d_density, const double *d_x, int64_t P,
               int flags, double *d_out, void *d_work, void *stream);
 
-/* measurement helpers (used by bench.py to obtain the FP64 roofline denominators) -------------- */
+/* measurement helpers (used by bench.py) ------------------------------------------------------- */
+/* Kernel launches issued by the library since the last reset (host-side count; graph replays of a
+ * captured sequence are not seen here -- bench.py multiplies the eager count). */
+int64_t bhs_launch_count(int reset);
+/* Per-category device timing: bhs_profile(1) clears and enables CUDA-event brackets around the launch
+ * groups below (not usable during graph capture), bhs_profile(0) disables.  bhs_profile_read
+ * synchronises and returns the summed milliseconds, the summed algorithmic work (flops or bytes, see
+ * DESIGN.md) and the number of brackets of one category. */
+#define BHS_PROF_LU_GEMM 0      /* zgemm_sub_kernel launches (work = 8 M N K flops)              */
+#define BHS_PROF_LU_PANEL 1     /* tournament pivoting + swaps + diagonal LU + L21                */
+#define BHS_PROF_LU_TRSM 2      /* U12 triangular solves                                          */
+#define BHS_PROF_LU_PACK 3      /* operand packing for the DMMA kernel                            */
+#define BHS_PROF_LU_RHS 4       /* forward / backward substitution of the right-hand sides        */
+#define BHS_PROF_ASM_MAIN 5     /* assemble_kernel (work = 16 N^2 bytes)                          */
+#define BHS_PROF_ASM_PRE 6      /* radial tables, pair harmonics, factors                         */
+#define BHS_PROF_USCAT 7        /* field kernel (work = 8 P B H flops)                            */
+#define BHS_PROF_RHS_EXPAND 8   /* right-hand-side expansion                                      */
+#define BHS_PROF_NCAT 9
+int bhs_profile(int enable);
+int bhs_profile_read(int category, double *ms, double *work, int64_t *count);
+
 /* Runs a register-resident DFMA loop / DMMA loop on every SM; returns achieved TFLOP/s. shape:
  * 0 = DFMA, 1 = mma.m8n8k4.f64, 2 = m16n8k4, 3 = m16n8k8, 4 = m16n8k16. */
 int bhs_fp64_peak(int shape, int iters, double *tflops_out);
