@@ -6,6 +6,12 @@ Re-exports the reference's public names (src/biem_helmholtz_sphere/__init__.py:2
 
 __version__ = "1.2.0+b200.1"
 
+import os as _os
+
+# k-sweeps keep up to 32 independent systems in flight on their own streams; give the driver enough hardware
+# queues (default 8) so those streams do not alias.  Only effective before the CUDA context exists.
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 from ._biem import (
     BIEMKwargs,
     BIEMResultCalculator,
