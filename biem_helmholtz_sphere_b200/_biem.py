@@ -390,18 +390,20 @@ class SweepEngine:
                     _ops.zgesv_(s.A, s.rhs, s.bufs)
                 elif not self.use_graphs:
                     self._body(s, True)
-                elif s.graph is None:
-                    self._body(s, True)  # eager run of the first system also warms every kernel up
-                else:
+                elif s.graph is not None:
                     s.graph.replay()
+                elif not s.warm:
+                    self._body(s, True)  # first use of the slot: eager run, which also warms every kernel up
+                    s.warm = True
+                else:
+                    # second use (in this or a later sweep): capture the (assembly -> LU) sequence once, then replay
+                    s.stream.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=s.stream):
+                        self._body(s, True)
+                    s.graph = g
+                    g.replay()
                 out_density[i].copy_(s.rhs, non_blocking=True)
-            if self.use_graphs and out_matrix is None and s.graph is None and K > len(self.slots):
-                # capture after the eager run; replays start with this slot's next system
-                s.stream.synchronize()
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=s.stream):
-                    self._body(s, True)
-                s.graph = g
         for s in self.slots:
             done = torch.cuda.Event()
             done.record(s.stream)

@@ -49,12 +49,15 @@ __global__ void uscat_coef_generic_kernel(int d, int L, int H, int B, double k, 
     if (far) c = cmul_ipow(c, -n);
     coefg[i] = c;
 }
-// 3-D records: per ball [c0, c1, c2, rho] then for (m, n>=m): (c_{n,+m}, c_{n,-m}) * SD_n * norm_{n,m}
-__global__ void uscat_coef3d_kernel(int L, int B, double k, double eta, int far, const double* __restrict__ centers,
-                                    const double* __restrict__ radii, const double4* __restrict__ rad,
-                                    const double* __restrict__ norm, const cplx* __restrict__ density,
-                                    double* __restrict__ rec) {
-    const int npair = L * (L + 1) / 2;
+// 3-D records, m-major over the PADDED band LMAX (multiple of 8, >= L): per ball [c0, c1, c2, rho] then for
+// (m, n = m..LMAX-1): (c_{n,+m}, c_{n,-m}) * SD_n * norm_{n,m}, zero for n >= L.  Block 0 also writes the
+// recurrence coefficients beta_{n,m} = (n^2 - m^2) / (4 n^2 - 1) in the same (m, n) order.
+__global__ void uscat_coef3d_kernel(int L, int LMAX, int B, double k, double eta, int far,
+                                    const double* __restrict__ centers, const double* __restrict__ radii,
+                                    const double4* __restrict__ rad, const double* __restrict__ norm,
+                                    const cplx* __restrict__ density, double* __restrict__ rec,
+                                    double* __restrict__ beta) {
+    const int npair = LMAX * (LMAX + 1) / 2;
     const int64_t stride = 4 + 4 * (int64_t)npair;
     int b = blockIdx.x;
     double* rb = rec + stride * b;
@@ -63,39 +66,57 @@ __global__ void uscat_coef3d_kernel(int L, int B, double k, double eta, int far,
     for (int e = threadIdx.x; e < npair; e += blockDim.x) {
         // decode (m, n) from the m-major running index
         int m = 0, off = 0;
-        while (off + (L - m) <= e) { off += L - m; ++m; }
+        while (off + (LMAX - m) <= e) { off += LMAX - m; ++m; }
         int n = m + (e - off);
-        double4 r = rad[(int64_t)b * L + n];
-        cplx sd = cscale(sd_coef(3, k, eta, radii[b], r.x, r.y), norm[e]);
-        if (far) sd = cmul_ipow(sd, -n);
-        cplx cp = cmul(density[(int64_t)b * H + n * n + m], sd);
-        cplx cm = (m == 0) ? cmake(0.0, 0.0) : cmul(density[(int64_t)b * H + n * n + 2 * n + 1 - m], sd);
-        reinterpret_cast<double4*>(rb + 4)[e] = make_double4(cp.x, cp.y, cm.x, cm.y);
+        if (b == 0) beta[e] = (double)(n * n - m * m) / (double)(4 * n * n - 1);
+        double4 out = make_double4(0.0, 0.0, 0.0, 0.0);
+        if (n < L) {
+            double4 r = rad[(int64_t)b * L + n];
+            const int eL = m * L - m * (m - 1) / 2 + (n - m);
+            cplx sd = cscale(sd_coef(3, k, eta, radii[b], r.x, r.y), norm[eL]);
+            if (far) sd = cmul_ipow(sd, -n);
+            cplx cp = cmul(density[(int64_t)b * H + n * n + m], sd);
+            cplx cm = (m == 0) ? cmake(0.0, 0.0) : cmul(density[(int64_t)b * H + n * n + 2 * n + 1 - m], sd);
+            out = make_double4(cp.x, cp.y, cm.x, cm.y);
+        }
+        reinterpret_cast<double4*>(rb + 4)[e] = out;
     }
 }
 
 // ---- 3-D fast kernel --------------------------------------------------------------------------------
-#define US_STEP(N)                                                              \
-    case N: {                                                                   \
-        if (N >= L) break;                                                      \
-        const double4 cc = recs[idx];                                           \
-        const double bt = sbeta[idx];                                           \
-        const double gr = hr[N] * q1, gi = hi[N] * q1;                          \
+// One step n = N of the Legendre recurrence at fixed m (entered Duff-style at case m).  The two recurrence
+// registers swap roles with the parity of N so that no register moves are needed; every index is a
+// compile-time immediate on top of the per-m base pointers.
+#define US_ACC(Q)                                                               \
+    {                                                                           \
+        const double gr = hr[(N_) < LMAX ? (N_) : 0] * (Q);                     \
+        const double gi = hi[(N_) < LMAX ? (N_) : 0] * (Q);                     \
         tpr = fma(gr, cc.x, tpr); tpi = fma(gr, cc.y, tpi);                     \
         tmr = fma(gr, cc.z, tmr); tmi = fma(gr, cc.w, tmi);                     \
         tpr = fma(-gi, cc.y, tpr); tpi = fma(gi, cc.x, tpi);                    \
         tmr = fma(-gi, cc.w, tmr); tmi = fma(gi, cc.z, tmi);                    \
-        const double qn = fma(ct, q1, -(bt * q0));                              \
-        q0 = q1; q1 = qn; ++idx;                                                \
     }
+#define US_STEP(N)                                                              \
+    us_l##N:                                                                    \
+        if ((N) < LMAX) {                                                       \
+            constexpr int N_ = (N);                                             \
+            const double4 cc = recs_m[N_];                                      \
+            const double bt = beta_m[N_];                                       \
+            if ((N_ & 1) == 0) {                                                \
+                US_ACC(qa)                                                      \
+                qb = fma(ct, qa, -(bt * qb));                                   \
+            } else {                                                            \
+                US_ACC(qb)                                                      \
+                qa = fma(ct, qb, -(bt * qa));                                   \
+            }                                                                   \
+        }
 
 template <int LMAX>
 __global__ void __launch_bounds__(US3D_THREADS) uscat3d_kernel(UscatArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int L = a.L, B = a.B;
-    const int npair = L * (L + 1) / 2;
-    const int rec_doubles = 4 + 4 * npair;
-    const uint32_t stage_bytes = (uint32_t)(US3D_CB * rec_doubles * sizeof(double));
+    constexpr int npair = LMAX * (LMAX + 1) / 2;
+    constexpr int rec_doubles = 4 + 4 * npair;
     double* stage0 = reinterpret_cast<double*>(smem_raw);
     double* stage1 = stage0 + US3D_CB * rec_doubles;
     double* sbeta = stage1 + US3D_CB * rec_doubles;
@@ -116,7 +137,6 @@ __global__ void __launch_bounds__(US3D_THREADS) uscat3d_kernel(UscatArgs a) {
         mbar_expect_tx(&full[0], bytes);
         tma_load_1d(stage0, a.rec, bytes, &full[0]);
     }
-    (void)stage_bytes;
 
     const int64_t p = (int64_t)blockIdx.x * US3D_THREADS + tid;
     const bool active = p < a.P;
@@ -170,6 +190,7 @@ __global__ void __launch_bounds__(US3D_THREADS) uscat3d_kernel(UscatArgs a) {
                 if (LMAX > 1) { hr[1] = (s * iz - co) * iz; hi[1] = (-co * iz - s) * iz; }
 #pragma unroll
                 for (int n = 1; n < LMAX - 1; ++n) {
+                    // orders n >= L only ever meet zero coefficients; clamp them so that nothing overflows
                     if (n + 1 < L) {
                         const double cf = (2 * n + 1) * iz;
                         hr[n + 1] = fma(cf, hr[n], -hr[n - 1]);
@@ -181,34 +202,171 @@ __global__ void __launch_bounds__(US3D_THREADS) uscat3d_kernel(UscatArgs a) {
             }
             double br = 0.0, bi = 0.0;   // this ball's sum
             double qmm = 1.0, cm = 1.0, sm = 0.0;
-            int idx = 0;
             for (int m = 0; m < L; ++m) {
-                double q0 = 0.0, q1 = qmm;
+                // q_{m-1} = 0, q_m = sin^m; the register holding the current value depends on the parity of m
+                double qa = (m & 1) ? 0.0 : qmm, qb = (m & 1) ? qmm : 0.0;
                 double tpr = 0.0, tpi = 0.0, tmr = 0.0, tmi = 0.0;
-                switch (m) {
-                    US_STEP(0) US_STEP(1) US_STEP(2) US_STEP(3) US_STEP(4) US_STEP(5) US_STEP(6) US_STEP(7)
-#if 1
-                    default: break;
-#endif
-                }
-                if (LMAX > 8) {
-                    switch (m < 8 ? 8 : m) {
-                        US_STEP(8) US_STEP(9) US_STEP(10) US_STEP(11) US_STEP(12) US_STEP(13) US_STEP(14) US_STEP(15)
-                        default: break;
+                const int off = m * LMAX - (m * (m - 1)) / 2 - m;
+                const double4* recs_m = recs + off;
+                const double* beta_m = sbeta + off;
+                // binary dispatch to the Duff entry point n = m (a switch compiles to a linear compare chain here)
+                if (m < 16) {
+                    if (m < 8) {
+                        if (m < 4) {
+                            if (m < 2) {
+                                if (m < 1) {
+                                    goto us_l0;
+                                } else {
+                                    goto us_l1;
+                                }
+                            } else {
+                                if (m < 3) {
+                                    goto us_l2;
+                                } else {
+                                    goto us_l3;
+                                }
+                            }
+                        } else {
+                            if (m < 6) {
+                                if (m < 5) {
+                                    goto us_l4;
+                                } else {
+                                    goto us_l5;
+                                }
+                            } else {
+                                if (m < 7) {
+                                    goto us_l6;
+                                } else {
+                                    goto us_l7;
+                                }
+                            }
+                        }
+                    } else {
+                        if (m < 12) {
+                            if (m < 10) {
+                                if (m < 9) {
+                                    goto us_l8;
+                                } else {
+                                    goto us_l9;
+                                }
+                            } else {
+                                if (m < 11) {
+                                    goto us_l10;
+                                } else {
+                                    goto us_l11;
+                                }
+                            }
+                        } else {
+                            if (m < 14) {
+                                if (m < 13) {
+                                    goto us_l12;
+                                } else {
+                                    goto us_l13;
+                                }
+                            } else {
+                                if (m < 15) {
+                                    goto us_l14;
+                                } else {
+                                    goto us_l15;
+                                }
+                            }
+                        }
+                    }
+                } else {
+                    if (m < 24) {
+                        if (m < 20) {
+                            if (m < 18) {
+                                if (m < 17) {
+                                    goto us_l16;
+                                } else {
+                                    goto us_l17;
+                                }
+                            } else {
+                                if (m < 19) {
+                                    goto us_l18;
+                                } else {
+                                    goto us_l19;
+                                }
+                            }
+                        } else {
+                            if (m < 22) {
+                                if (m < 21) {
+                                    goto us_l20;
+                                } else {
+                                    goto us_l21;
+                                }
+                            } else {
+                                if (m < 23) {
+                                    goto us_l22;
+                                } else {
+                                    goto us_l23;
+                                }
+                            }
+                        }
+                    } else {
+                        if (m < 28) {
+                            if (m < 26) {
+                                if (m < 25) {
+                                    goto us_l24;
+                                } else {
+                                    goto us_l25;
+                                }
+                            } else {
+                                if (m < 27) {
+                                    goto us_l26;
+                                } else {
+                                    goto us_l27;
+                                }
+                            }
+                        } else {
+                            if (m < 30) {
+                                if (m < 29) {
+                                    goto us_l28;
+                                } else {
+                                    goto us_l29;
+                                }
+                            } else {
+                                if (m < 31) {
+                                    goto us_l30;
+                                } else {
+                                    goto us_l31;
+                                }
+                            }
+                        }
                     }
                 }
-                if (LMAX > 16) {
-                    switch (m < 16 ? 16 : m) {
-                        US_STEP(16) US_STEP(17) US_STEP(18) US_STEP(19) US_STEP(20) US_STEP(21) US_STEP(22) US_STEP(23)
-                        default: break;
-                    }
-                }
-                if (LMAX > 24) {
-                    switch (m < 24 ? 24 : m) {
-                        US_STEP(24) US_STEP(25) US_STEP(26) US_STEP(27) US_STEP(28) US_STEP(29) US_STEP(30) US_STEP(31)
-                        default: break;
-                    }
-                }
+                US_STEP(0)
+                US_STEP(1)
+                US_STEP(2)
+                US_STEP(3)
+                US_STEP(4)
+                US_STEP(5)
+                US_STEP(6)
+                US_STEP(7)
+                US_STEP(8)
+                US_STEP(9)
+                US_STEP(10)
+                US_STEP(11)
+                US_STEP(12)
+                US_STEP(13)
+                US_STEP(14)
+                US_STEP(15)
+                US_STEP(16)
+                US_STEP(17)
+                US_STEP(18)
+                US_STEP(19)
+                US_STEP(20)
+                US_STEP(21)
+                US_STEP(22)
+                US_STEP(23)
+                US_STEP(24)
+                US_STEP(25)
+                US_STEP(26)
+                US_STEP(27)
+                US_STEP(28)
+                US_STEP(29)
+                US_STEP(30)
+                US_STEP(31)
                 // (T+ e^{i m phi} + T- e^{-i m phi})
                 br += (tpr + tmr) * cm - (tpi - tmi) * sm;
                 bi += (tpi + tmi) * cm + (tpr - tmr) * sm;
@@ -348,9 +506,9 @@ static inline int64_t align256(int64_t v) { return (v + 255) & ~(int64_t)255; }
 
 extern "C" int64_t bhs_uscat_workspace(const bhs_plan_t* plan, int B) {
     if (!plan || B <= 0) return BHS_ERR_INVALID;
-    int64_t L = plan->n_end, npair = L * (L + 1) / 2;
+    int64_t L = plan->n_end, LM = (L + 7) / 8 * 8, npair = LM * (LM + 1) / 2;
     int64_t rad = align256((int64_t)B * L * sizeof(double4));
-    int64_t c3 = align256((int64_t)B * (4 + 4 * npair) * sizeof(double));
+    int64_t c3 = align256((int64_t)B * (4 + 4 * npair) * sizeof(double)) + align256(npair * sizeof(double));
     int64_t cg = align256((int64_t)B * plan->H * sizeof(cplx));
     int64_t kbuf = 256;
     return rad + (c3 > cg ? c3 : cg) + kbuf;
@@ -358,7 +516,7 @@ extern "C" int64_t bhs_uscat_workspace(const bhs_plan_t* plan, int B) {
 
 template <int LMAX>
 static int launch_uscat3d(const UscatArgs& a, cudaStream_t st) {
-    const int npair = a.L * (a.L + 1) / 2;
+    const int npair = LMAX * (LMAX + 1) / 2;
     size_t smem = (size_t)(2 * US3D_CB * (4 + 4 * npair) + npair) * sizeof(double);
     cudaFuncSetAttribute(uscat3d_kernel<LMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int64_t blocks = (a.P + US3D_THREADS - 1) / US3D_THREADS;
@@ -391,10 +549,14 @@ extern "C" int bhs_uscat(const bhs_plan_t* plan, int B, const double* d_centers,
     a.coefg = nullptr; a.rec = nullptr; a.beta = plan->d_us_beta; a.idx = plan->d_idx; a.deg = plan->d_deg;
     a.out = (cplx*)d_out;
     if (d == 3 && L <= 32) {
-        uscat_coef3d_kernel<<<B, 128, 0, st>>>(L, B, k, eta, far, d_centers, d_radii, d_rad, plan->d_us_norm,
-                                               (const cplx*)d_density, (double*)d_coef);
+        const int LM = (L + 7) / 8 * 8;
+        const int64_t npm = (int64_t)LM * (LM + 1) / 2;
+        double* d_beta = (double*)(d_coef + align256((int64_t)B * (4 + 4 * npm) * sizeof(double)));
+        uscat_coef3d_kernel<<<B, 128, 0, st>>>(L, LM, B, k, eta, far, d_centers, d_radii, d_rad, plan->d_us_norm,
+                                               (const cplx*)d_density, (double*)d_coef, d_beta);
         BHS_CHECK_LAUNCH();
         a.rec = (const double*)d_coef;
+        a.beta = d_beta;
         (void)npair;
         if (L <= 8) return launch_uscat3d<8>(a, st);
         if (L <= 16) return launch_uscat3d<16>(a, st);

@@ -1,0 +1,52 @@
+"""C5-shaped end-to-end run (8x8 sphere grid, field heat map) at a size the oracle can follow, plus the
+size-independent checks that tools/bench_c5.py applies at the full N = 36 864."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+pytestmark = pytest.mark.gpu
+
+
+def test_c5_reduced_against_oracle():
+    import torch
+
+    import bench_c5
+    from biem_helmholtz_sphere_b200.geometry import field_grid, grid_centers
+    from oracle import biem_oracle as O
+
+    half, n_end, grid = 2, 10, 48
+    out, dens = bench_c5.run(half, n_end, 1.0, grid)
+    assert out["lu_info"] == 0
+    assert out["solve_rel_residual"] < 1e-13
+    assert out["bc_residual_max"] < 1e-6  # truncation error of n_end = 10 at k = 1 (not a round-off figure)
+    cen = grid_centers(half, 3)
+    uin, _ = O.plane_wave(k=1.0, direction=np.array([1.0, 0.0, 0.0]))
+    ref = O.biem("ba", centers=cen, radii=np.ones(len(cen)), k=1.0, n_end=n_end, uin=uin, eta=1.0)
+    d = dens.cpu().numpy()
+    err_d = np.max(np.abs(d - ref.density)) / np.max(np.abs(ref.density))
+    assert err_d < 1e-10, err_d
+    x = field_grid(grid, 20.0, 3)
+    want = ref.uscat(x)
+    from biem_helmholtz_sphere_b200 import _ops
+
+    got = _ops.uscat(3, n_end, cen, np.ones(len(cen)), 1.0, 1.0, dens, x.reshape(3, -1)).cpu().numpy().reshape(grid, grid)
+    nan_w = np.isnan(want)
+    assert np.array_equal(nan_w, np.isnan(got)) and nan_w.any()
+    err_u = np.max(np.abs(got[~nan_w] - want[~nan_w])) / np.max(np.abs(want[~nan_w]))
+    print(f"\nC5-reduced: density rel err {err_d:.2e}, field rel err {err_u:.2e}, bc {out['bc_residual_max']:.2e}")
+    assert err_u < 1e-10
+
+
+def test_c5_size_independent_checks_n_end_24():
+    """Full n_end = 24 harmonics on a 2x2 sphere grid (N = 2304): residual and boundary condition at round-off level."""
+    import bench_c5
+
+    out, _ = bench_c5.run(1, 24, 1.0, 32)
+    assert out["lu_info"] == 0
+    assert out["solve_rel_residual"] < 1e-13
+    assert out["bc_residual_max"] < 1e-10
