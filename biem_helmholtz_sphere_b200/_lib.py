@@ -49,7 +49,7 @@ SIGNATURES = {
 }
 
 KIND_J, KIND_Y, KIND_H1 = 0, 1, 2
-PROF_CATEGORIES = ("lu_gemm", "lu_panel", "lu_trsm", "lu_pack", "lu_rhs", "asm_main", "asm_pre", "uscat", "rhs_expand")
+PROF_CATEGORIES = ("lu_gemm", "lu_panel", "lu_trsm", "lu_pack", "lu_rhs", "asm_main", "asm_pre", "uscat", "rhs_expand", "lu_gemm_inner")
 FLAG_PER_BALL, FLAG_FAR_FIELD, FLAG_INNER = 1, 2, 4
 
 

@@ -37,6 +37,112 @@ __global__ void pair_vectors_kernel(int d, int B, const double* __restrict__ cen
     dist[i] = sqrt(r2);
 }
 
+// ---- translation-vector de-duplication --------------------------------------------------------------
+// The (S|R)(t) block depends on the pair (b, b') only through t = c_b - c_b'.  Regular geometries repeat the
+// same t many times (4x4 grid: 48 distinct t among 240 ordered pairs; 8x8 grid: 224 among 4032), so the
+// contraction is done once per DISTINCT t and the result is scaled and written for every pair that shares it.
+// rep[i] = smallest pair index with bit-identical t (exact comparison: irregular geometries simply get U = np - B).
+__global__ void pair_rep_kernel(int d, int B, int dedupe, const double* __restrict__ tv, int32_t* __restrict__ rep) {
+    const int np = B * B;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= np) return;
+    if (i / B == i % B) { rep[i] = -1; return; }
+    if (!dedupe) { rep[i] = i; return; }
+    double t[BHS_MAX_NODES + 2];
+    for (int a = 0; a < d; ++a) t[a] = tv[(int64_t)a * np + i];
+    int r = i;
+    for (int j = 0; j < i; ++j) {
+        if (j / B == j % B) continue;
+        bool same = true;
+        for (int a = 0; a < d; ++a) same = same && (tv[(int64_t)a * np + j] == t[a]);
+        if (same) { r = j; break; }
+    }
+    rep[i] = r;
+}
+// Single CTA: number the distinct translations and bucket the pairs.
+//   n_unique[0] = U;  grp_rep[u] = representative pair;  grp_start[u..u+1) -> members[] (pair ids)
+// uid[] and cursor[] are scratch of np ints each.
+__global__ void __launch_bounds__(1024) pair_group_kernel(int B, const int32_t* __restrict__ rep, int32_t* __restrict__ uid,
+                                                          int32_t* __restrict__ cursor, int32_t* __restrict__ n_unique,
+                                                          int32_t* __restrict__ grp_rep, int32_t* __restrict__ grp_start,
+                                                          int32_t* __restrict__ members) {
+    __shared__ int s_scan[1024];
+    __shared__ int s_base;
+    const int np = B * B, tid = threadIdx.x, T = blockDim.x;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    // pass 1: uid[i] = index of pair i among the representatives (exclusive scan of the flags), chunk by chunk
+    for (int c0 = 0; c0 < np; c0 += T) {
+        const int i = c0 + tid;
+        const int flag = (i < np && rep[i] == i) ? 1 : 0;
+        s_scan[tid] = flag;
+        __syncthreads();
+        for (int o = 1; o < T; o <<= 1) {
+            int v = (tid >= o) ? s_scan[tid - o] : 0;
+            __syncthreads();
+            s_scan[tid] += v;
+            __syncthreads();
+        }
+        const int incl = s_scan[tid], base = s_base;
+        if (flag) {
+            uid[i] = base + incl - 1;
+            grp_rep[base + incl - 1] = i;
+        }
+        __syncthreads();
+        if (tid == T - 1) s_base = base + incl;
+        __syncthreads();
+    }
+    const int U = s_base;
+    if (tid == 0) n_unique[0] = U;
+    for (int u = tid; u <= U; u += T) { cursor[u] = 0; }
+    __syncthreads();
+    // pass 2: group sizes
+    for (int i = tid; i < np; i += T)
+        if (rep[i] >= 0) atomicAdd(&cursor[uid[rep[i]]], 1);
+    __syncthreads();
+    // pass 3: exclusive scan of the sizes -> grp_start (serial over chunks as above)
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < U; c0 += T) {
+        const int u = c0 + tid;
+        const int cnt = (u < U) ? cursor[u] : 0;
+        s_scan[tid] = cnt;
+        __syncthreads();
+        for (int o = 1; o < T; o <<= 1) {
+            int v = (tid >= o) ? s_scan[tid - o] : 0;
+            __syncthreads();
+            s_scan[tid] += v;
+            __syncthreads();
+        }
+        const int incl = s_scan[tid], base = s_base;
+        if (u < U) grp_start[u] = base + incl - cnt;
+        __syncthreads();
+        if (tid == T - 1) s_base = base + incl;
+        __syncthreads();
+    }
+    if (tid == 0) grp_start[U] = s_base;
+    for (int u = tid; u < U; u += T) cursor[u] = 0;
+    __syncthreads();
+    // pass 4: fill (order inside a group is irrelevant: every member gets the same block)
+    for (int i = tid; i < np; i += T)
+        if (rep[i] >= 0) {
+            const int u = uid[rep[i]];
+            members[grp_start[u] + atomicAdd(&cursor[u], 1)] = i;
+        }
+}
+
+// diagonal blocks A[(b,h),(b,h')] = delta_{hh'} diag[s][b][h]
+__global__ void diag_blocks_kernel(int B, int H, const cplx* __restrict__ diag, cplx* __restrict__ A, int64_t ld,
+                                   int64_t sys_stride) {
+    const int sys = blockIdx.z, b = blockIdx.y;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)H * H) return;
+    const int h = (int)(e / H), hp = (int)(e % H);
+    cplx v = cmake(0.0, 0.0);
+    if (h == hp) v = diag[((int64_t)sys * B + b) * H + h];
+    A[(int64_t)sys * sys_stride + ((int64_t)b * H + h) * ld + (int64_t)b * H + hp] = v;
+}
+
 struct SmArrA {
     double* p;
     int stride;
@@ -92,7 +198,11 @@ __global__ void factors_kernel(int d, int L, int H, int B, int nsys, const doubl
 
 // ---- the assembly kernel --------------------------------------------------------------------------------
 struct AsmArgs {
-    int B, H, H2, L2, nt_res, pairs_per_cta;
+    int B, H, H2, L2, nt_res;
+    const int32_t* n_unique;   // [1]   number of distinct translation vectors U
+    const int32_t* grp_rep;    // [U]   representative pair of each
+    const int32_t* grp_start;  // [U+1] member ranges
+    const int32_t* members;    // pair ids (b * B + b') bucketed by translation
     const bhs_tile_hdr* tiles;
     const double* coef;
     const uint16_t* cidx;
@@ -141,53 +251,54 @@ __global__ void __launch_bounds__(ASM_THREADS) assemble_kernel(AsmArgs a) {
     const int h1 = tr * BHS_TILE_R + r1, hp1 = tc * BHS_TILE_C + c1;
     const bool ok0 = h0 < a.H && hp0 < a.H, ok1 = h1 < a.H && hp1 < a.H;
     const int64_t npairs = (int64_t)a.B * a.B;
-    const int64_t p_begin = (int64_t)blockIdx.y * a.pairs_per_cta;
-    const int64_t p_end = min(npairs, p_begin + a.pairs_per_cta);
     cplx* Asys = a.A + (int64_t)sys * a.sys_stride;
     const cplx* rowf = a.rowf + (int64_t)sys * a.B * a.H;
     const cplx* colf = a.colf + (int64_t)sys * a.B * a.H;
-    const cplx* diag = a.diag + (int64_t)sys * a.B * a.H;
+    const int U = a.n_unique[0];
 
-    for (int64_t pr = p_begin; pr < p_end; ++pr) {
-        const int b = (int)(pr / a.B), bp = (int)(pr % a.B);
-        cplx v0 = cmake(0.0, 0.0), v1 = cmake(0.0, 0.0);
-        if (b == bp) {
-            if (ok0 && h0 == hp0) v0 = diag[(int64_t)b * a.H + h0];
-            if (ok1 && h1 == hp1) v1 = diag[(int64_t)b * a.H + h1];
-        } else {
-            // S_{h''}(t) for the index window this tile references
-            const cplx* y2 = a.Y2 + pr * a.H2 + hd.sy_lo;
-            const cplx* hpw = a.hp + ((int64_t)sys * npairs + pr) * a.L2;
-            const int32_t* dg = a.deg2 + hd.sy_lo;
-            for (int j = tid; j < hd.sy_cnt; j += ASM_THREADS) s_sy[j] = cmul(y2[j], hpw[dg[j]]);
-            __syncthreads();
-            double ar0 = 0.0, ai0 = 0.0, ar1 = 0.0, ai1 = 0.0;
-            for (int t0 = 0; t0 < nt; t0 += nt_res) {
-                const int tn = min(nt_res, nt - t0);
-                if (!resident) {
-                    if (tid == 0) {
-                        fence_proxy_async();
-                        mbar_expect_tx(&bar, (uint32_t)(tn * (ASM_LAYER_COEF + ASM_LAYER_IDX)));
-                        tma_load_1d(s_coef, a.coef + hd.coef_off + (int64_t)t0 * BHS_TILE_E, (uint32_t)(tn * ASM_LAYER_COEF), &bar);
-                        tma_load_1d(s_idx, a.cidx + hd.idx_off + (int64_t)t0 * BHS_TILE_E, (uint32_t)(tn * ASM_LAYER_IDX), &bar);
-                    }
-                    mbar_wait(&bar, phase);
-                    phase ^= 1;
+    // distinct translations u = blockIdx.y, blockIdx.y + gridDim.y, ...: contract once, write for every member pair
+    for (int u = blockIdx.y; u < U; u += gridDim.y) {
+        const int64_t pr = a.grp_rep[u];
+        // S_{h''}(t) for the index window this tile references
+        const cplx* y2 = a.Y2 + pr * a.H2 + hd.sy_lo;
+        const cplx* hpw = a.hp + ((int64_t)sys * npairs + pr) * a.L2;
+        const int32_t* dg = a.deg2 + hd.sy_lo;
+        for (int j = tid; j < hd.sy_cnt; j += ASM_THREADS) s_sy[j] = cmul(y2[j], hpw[dg[j]]);
+        __syncthreads();
+        double ar0 = 0.0, ai0 = 0.0, ar1 = 0.0, ai1 = 0.0;
+        for (int t0 = 0; t0 < nt; t0 += nt_res) {
+            const int tn = min(nt_res, nt - t0);
+            if (!resident) {
+                if (tid == 0) {
+                    fence_proxy_async();
+                    mbar_expect_tx(&bar, (uint32_t)(tn * (ASM_LAYER_COEF + ASM_LAYER_IDX)));
+                    tma_load_1d(s_coef, a.coef + hd.coef_off + (int64_t)t0 * BHS_TILE_E, (uint32_t)(tn * ASM_LAYER_COEF), &bar);
+                    tma_load_1d(s_idx, a.cidx + hd.idx_off + (int64_t)t0 * BHS_TILE_E, (uint32_t)(tn * ASM_LAYER_IDX), &bar);
                 }
-#pragma unroll 4
-                for (int t = 0; t < tn; ++t) {
-                    const double cf0 = s_coef[t * BHS_TILE_E + e0], cf1 = s_coef[t * BHS_TILE_E + e1];
-                    const cplx s0 = s_sy[s_idx[t * BHS_TILE_E + e0]], s1 = s_sy[s_idx[t * BHS_TILE_E + e1]];
-                    ar0 = fma(cf0, s0.x, ar0); ai0 = fma(cf0, s0.y, ai0);
-                    ar1 = fma(cf1, s1.x, ar1); ai1 = fma(cf1, s1.y, ai1);
-                }
-                if (!resident) __syncthreads();  // everyone done with the chunk before it is overwritten
+                mbar_wait(&bar, phase);
+                phase ^= 1;
             }
-            if (ok0) v0 = cmul(cmul(cmake(ar0, ai0), rowf[(int64_t)b * a.H + h0]), colf[(int64_t)bp * a.H + hp0]);
-            if (ok1) v1 = cmul(cmul(cmake(ar1, ai1), rowf[(int64_t)b * a.H + h1]), colf[(int64_t)bp * a.H + hp1]);
+#pragma unroll 4
+            for (int t = 0; t < tn; ++t) {
+                const double cf0 = s_coef[t * BHS_TILE_E + e0], cf1 = s_coef[t * BHS_TILE_E + e1];
+                const cplx s0 = s_sy[s_idx[t * BHS_TILE_E + e0]], s1 = s_sy[s_idx[t * BHS_TILE_E + e1]];
+                ar0 = fma(cf0, s0.x, ar0); ai0 = fma(cf0, s0.y, ai0);
+                ar1 = fma(cf1, s1.x, ar1); ai1 = fma(cf1, s1.y, ai1);
+            }
+            if (!resident) __syncthreads();  // everyone done with the chunk before it is overwritten
         }
-        if (ok0) Asys[((int64_t)b * a.H + h0) * a.ld + (int64_t)bp * a.H + hp0] = v0;
-        if (ok1) Asys[((int64_t)b * a.H + h1) * a.ld + (int64_t)bp * a.H + hp1] = v1;
+        const cplx raw0 = cmake(ar0, ai0), raw1 = cmake(ar1, ai1);
+        const int q_end = a.grp_start[u + 1];
+        for (int q = a.grp_start[u]; q < q_end; ++q) {
+            const int prm = a.members[q];
+            const int b = prm / a.B, bp = prm % a.B;
+            if (ok0)
+                Asys[((int64_t)b * a.H + h0) * a.ld + (int64_t)bp * a.H + hp0] =
+                    cmul(cmul(raw0, rowf[(int64_t)b * a.H + h0]), colf[(int64_t)bp * a.H + hp0]);
+            if (ok1)
+                Asys[((int64_t)b * a.H + h1) * a.ld + (int64_t)bp * a.H + hp1] =
+                    cmul(cmul(raw1, rowf[(int64_t)b * a.H + h1]), colf[(int64_t)bp * a.H + hp1]);
+        }
         __syncthreads();  // s_sy reuse
     }
 }
@@ -204,6 +315,7 @@ struct AsmWork {
     cplx* rowf;
     cplx* colf;
     cplx* diag;
+    int32_t *rep, *uid, *cursor, *n_unique, *grp_rep, *grp_start, *members;
     int64_t bytes;
 };
 static AsmWork carve(const bhs_plan* p, int B, int nsys, void* base) {
@@ -219,6 +331,13 @@ static AsmWork carve(const bhs_plan* p, int B, int nsys, void* base) {
     w.rowf = (cplx*)take((int64_t)nsys * B * p->H * sizeof(cplx));
     w.colf = (cplx*)take((int64_t)nsys * B * p->H * sizeof(cplx));
     w.diag = (cplx*)take((int64_t)nsys * B * p->H * sizeof(cplx));
+    w.rep = (int32_t*)take(np * 4);
+    w.uid = (int32_t*)take(np * 4);
+    w.cursor = (int32_t*)take((np + 1) * 4);
+    w.n_unique = (int32_t*)take(256);
+    w.grp_rep = (int32_t*)take(np * 4);
+    w.grp_start = (int32_t*)take((np + 1) * 4);
+    w.members = (int32_t*)take(np * 4);
     w.bytes = off;
     return w;
 }
@@ -274,8 +393,14 @@ extern "C" int bhs_assemble(const bhs_plan_t* plan, int B, int nsys, const doubl
         pair_radial_kernel<<<(unsigned)blocks, T, smem, st>>>(d, plan->L2, n_store, B, nsys, d_k, w.dist, w.hp);
         BHS_CHECK_LAUNCH();
     }
+    // the search is O(np^2) in the worst case (no duplicates): bounded by skipping it for more than 128 spheres
+    pair_rep_kernel<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(plan->d, B, B <= 128 ? 1 : 0, w.tv, w.rep);
+    BHS_CHECK_LAUNCH();
+    pair_group_kernel<<<1, 1024, 0, st>>>(B, w.rep, w.uid, w.cursor, w.n_unique, w.grp_rep, w.grp_start, w.members);
+    BHS_CHECK_LAUNCH();
     AsmArgs a;
     a.B = B; a.H = plan->H; a.H2 = plan->H2; a.L2 = plan->L2;
+    a.n_unique = w.n_unique; a.grp_rep = w.grp_rep; a.grp_start = w.grp_start; a.members = w.members;
     a.tiles = plan->d_tiles; a.coef = plan->d_coef; a.cidx = plan->d_cidx; a.deg2 = plan->d_deg2;
     a.Y2 = w.Y2; a.hp = w.hp; a.rowf = w.rowf; a.colf = w.colf; a.diag = w.diag;
     a.A = (cplx*)d_A; a.ld = ld; a.sys_stride = sys_stride;
@@ -288,22 +413,26 @@ extern "C" int bhs_assemble(const bhs_plan_t* plan, int B, int nsys, const doubl
     size_t smem = (size_t)a.nt_res * (ASM_LAYER_COEF + ASM_LAYER_IDX) + sy_bytes;
     cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int ntiles = plan->tiles_r * plan->tiles_c;
-    // pair chunks: enough CTAs to fill the machine a few times over, at least 8 pairs per CTA
-    int64_t want_ctas = 148 * 8;
-    int64_t chunks = (want_ctas + (int64_t)ntiles * nsys - 1) / ((int64_t)ntiles * nsys);
+    // The number of distinct translations U is only known on the device: the y-dimension strides over them, sized
+    // for about four waves of CTAs (2 resident per SM) and never more than the off-diagonal pair count.
+    int64_t chunks = (4 * 2 * 148 + (int64_t)ntiles * nsys - 1) / ((int64_t)ntiles * nsys);
     if (chunks < 1) chunks = 1;
-    int64_t ppc = (np + chunks - 1) / chunks;
-    if (ppc < 8) ppc = 8;
-    if (ppc > np) ppc = np;
-    chunks = (np + ppc - 1) / ppc;
-    a.pairs_per_cta = (int)ppc;
+    if (chunks > np - B) chunks = np - B > 0 ? np - B : 1;
     if (chunks > 65535 || nsys > 65535) return BHS_ERR_UNSUPPORTED;
     dim3 grid((unsigned)ntiles, (unsigned)chunks, (unsigned)nsys);
     bhs_prof_end(BHS_PROF_ASM_PRE, 0.0, st);
     bhs_prof_begin(BHS_PROF_ASM_MAIN, st);
-    assemble_kernel<<<grid, ASM_THREADS, smem, st>>>(a);
+    {
+        const int64_t hh = (int64_t)plan->H * plan->H;
+        dim3 dgrid((unsigned)((hh + 255) / 256), (unsigned)B, (unsigned)nsys);
+        diag_blocks_kernel<<<dgrid, 256, 0, st>>>(B, plan->H, w.diag, (cplx*)d_A, ld, sys_stride);
+        BHS_CHECK_LAUNCH();
+    }
+    if (B > 1) {
+        assemble_kernel<<<grid, ASM_THREADS, smem, st>>>(a);
+        BHS_CHECK_LAUNCH();
+    }
     bhs_prof_end(BHS_PROF_ASM_MAIN, 16.0 * (double)N * (double)N * nsys, st);
-    BHS_CHECK_LAUNCH();
     return BHS_OK;
 }
 

@@ -519,9 +519,10 @@ static void lu_gemm(LuCtx& x, int64_t r_lo, int64_t r_hi, int64_t c_lo, int64_t 
     int rt1 = (int)((r_hi - 1 - x.J) / G_TM), ct1 = (int)((c_hi - 1) / G_TN);
     g.row_lo = r_lo; g.row_hi = r_hi; g.col_lo = c_lo; g.col_hi = c_hi;
     dim3 grid(ct1 - g.ct0 + 1, rt1 - g.rt0 + 1);
-    bhs_prof_begin(BHS_PROF_LU_GEMM, x.st);
+    const int pcat = (K >= LU_NBO || (k0 == x.J && r_lo >= x.J + LU_NBO)) ? BHS_PROF_LU_GEMM : BHS_PROF_LU_GEMM_IN;
+    bhs_prof_begin(pcat, x.st);
     zgemm_sub_kernel<<<grid, G_THREADS, G_SMEM, x.st>>>(g);
-    bhs_prof_end(BHS_PROF_LU_GEMM, 8.0 * (double)(r_hi - r_lo) * (double)(c_hi - c_lo) * (double)K, x.st);
+    bhs_prof_end(pcat, 8.0 * (double)(r_hi - r_lo) * (double)(c_hi - c_lo) * (double)K, x.st);
     LU_LAUNCH_CHECK(x);
 }
 static void lu_pack_l(LuCtx& x, int64_t r_lo, int64_t r_hi, int64_t k0, int K) {

@@ -143,7 +143,8 @@ int64_t bhs_launch_count(int reset);
  * groups below (not usable during graph capture), bhs_profile(0) disables.  bhs_profile_read
  * synchronises and returns the summed milliseconds, the summed algorithmic work (flops or bytes, see
  * DESIGN.md) and the number of brackets of one category. */
-#define BHS_PROF_LU_GEMM 0      /* zgemm_sub_kernel launches (work = 8 M N K flops)              */
+#define BHS_PROF_LU_GEMM 0      /* zgemm_sub_kernel, trailing updates of the outer blocks, K = 128
+                                   (work = 8 M N K flops; 97.7 % of the flops of a factorisation)  */
 #define BHS_PROF_LU_PANEL 1     /* tournament pivoting + swaps + diagonal LU + L21                */
 #define BHS_PROF_LU_TRSM 2      /* U12 triangular solves                                          */
 #define BHS_PROF_LU_PACK 3      /* operand packing for the DMMA kernel                            */
@@ -152,7 +153,8 @@ int64_t bhs_launch_count(int reset);
 #define BHS_PROF_ASM_PRE 6      /* radial tables, pair harmonics, factors                         */
 #define BHS_PROF_USCAT 7        /* field kernel (work = 8 P B H flops)                            */
 #define BHS_PROF_RHS_EXPAND 8   /* right-hand-side expansion                                      */
-#define BHS_PROF_NCAT 9
+#define BHS_PROF_LU_GEMM_IN 9   /* zgemm_sub_kernel, K = 32 / 64 updates inside the panel recursion  */
+#define BHS_PROF_NCAT 10
 int bhs_profile(int enable);
 int bhs_profile_read(int category, double *ms, double *work, int64_t *count);
 

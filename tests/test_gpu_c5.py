@@ -43,10 +43,12 @@ def test_c5_reduced_against_oracle():
 
 
 def test_c5_size_independent_checks_n_end_24():
-    """Full n_end = 24 harmonics on a 2x2 sphere grid (N = 2304): residual and boundary condition at round-off level."""
+    """Full n_end = 24 harmonics on a 2x2 sphere grid (N = 2304): solve residual at round-off level; the boundary
+    condition is met to the aliasing error of the reference's n_end-point RHS quadrature (SURVEY 8c quirk ii),
+    3e-9 at the full C5 size."""
     import bench_c5
 
     out, _ = bench_c5.run(1, 24, 1.0, 32)
     assert out["lu_info"] == 0
     assert out["solve_rel_residual"] < 1e-13
-    assert out["bc_residual_max"] < 1e-10
+    assert out["bc_residual_max"] < 1e-7
