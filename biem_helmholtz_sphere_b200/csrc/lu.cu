@@ -128,7 +128,6 @@ __global__ void __launch_bounds__(G_THREADS, 2) zgemm_sub_kernel(GemmArgs g) {
 }
 
 static const size_t G_SMEM = (size_t)G_STAGES * (G_A_STAGE + G_B_STAGE) * sizeof(double);
-static const size_t LU_TILE_SMEM = (size_t)LU_R * (LU_NB + 1) * sizeof(cplx);
 
 // ---- packing -------------------------------------------------------------------------------------------
 // Lp tile (rt, stage): [64 rows][20] doubles, row r = interleaved complex A[row_base + 64 rt + r][k0 + 8 stage ..]
@@ -173,17 +172,31 @@ __global__ void pack_u_kernel(const cplx* __restrict__ A, int64_t ld, int64_t nc
 // One CTA eliminates up to LU_R candidate rows (one per thread, LU_NB complex in registers) with partial
 // pivoting and emits the rows it pivoted on, in order.  rows_in == nullptr: contiguous rows
 // [row_begin + 128*blockIdx.x, ...) ; otherwise rows_in[128*blockIdx.x + t] (-1 = empty slot).
+//
+// The LAST round of a panel (one CTA, fin.ipiv != nullptr) also finishes the panel's bookkeeping, so that no
+// single-thread / single-CTA kernels sit on the critical path:
+//   * the eliminated pivot rows ARE the factored diagonal block (multipliers left of the diagonal, U on and right of
+//     it): they are written to fin.dblk [w][LU_NB] and copied into A by the swap kernel;
+//   * the ordered pivot list is converted to LAPACK-style sequential swaps ipiv[j + c];
+//   * a zero pivot sets info = j + c + 1.
+struct SelectFinal {
+    int64_t j;
+    int32_t* ipiv;
+    int32_t* info;
+    cplx* dblk;
+};
+
 __global__ void __launch_bounds__(LU_R) lu_select_kernel(const cplx* __restrict__ A, int64_t ld, int64_t col0, int w,
                                                          const int32_t* __restrict__ rows_in, int64_t n_in,
                                                          int64_t row_begin, int64_t row_end,
-                                                         int32_t* __restrict__ rows_out) {
-    extern __shared__ __align__(16) unsigned char lu_dyn_smem[];
-    cplx (*tile)[LU_NB + 1] = reinterpret_cast<cplx (*)[LU_NB + 1]>(lu_dyn_smem);
+                                                         int32_t* __restrict__ rows_out, SelectFinal fin) {
     __shared__ cplx prow[LU_NB];
+    __shared__ cplx prinv;
     __shared__ double wmag[LU_R / 32];
     __shared__ int wlane[LU_R / 32];
-    __shared__ int s_rows[LU_R];
+    __shared__ int32_t s_win[LU_NB];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool is_final = fin.ipiv != nullptr;
     // which global row does this thread own?
     int64_t slot = (int64_t)blockIdx.x * LU_R + tid;
     int32_t myrow = -1;
@@ -193,19 +206,14 @@ __global__ void __launch_bounds__(LU_R) lu_select_kernel(const cplx* __restrict_
         int64_t r = row_begin + slot;
         if (r < row_end) myrow = (int32_t)r;
     }
-    s_rows[tid] = myrow;
-    __syncthreads();
-    // coalesced load: each warp reads whole rows
-    for (int rr = warp; rr < LU_R; rr += LU_R / 32) {
-        int32_t gr = s_rows[rr];
-        cplx v = cmake(0.0, 0.0);
-        if (gr >= 0 && lane < w) v = A[(int64_t)gr * ld + col0 + lane];
-        tile[rr][lane] = v;
-    }
-    __syncthreads();
+    // Each thread reads its own candidate row straight into registers (512 contiguous bytes per thread).  No
+    // shared-memory staging: a 67 KB tile would keep a second zgemm CTA of a concurrent system off this SM.
     cplx x[LU_NB];
+    {
+        const cplx* src = A + (int64_t)(myrow >= 0 ? myrow : 0) * ld + col0;
 #pragma unroll
-    for (int c = 0; c < LU_NB; ++c) x[c] = tile[tid][c];
+        for (int c = 0; c < LU_NB; ++c) x[c] = (myrow >= 0 && c < w) ? __ldg(src + c) : cmake(0.0, 0.0);
+    }
     bool active = myrow >= 0;
 #pragma unroll
     for (int c = 0; c < LU_NB; ++c) {
@@ -230,44 +238,54 @@ __global__ void __launch_bounds__(LU_R) lu_select_kernel(const cplx* __restrict_
             const bool any = best >= 0.0;  // at least one active row left
             if (any && tid == winner) {
 #pragma unroll
-                for (int j = 0; j < LU_NB; ++j) prow[j] = x[j];
+                for (int j = c; j < LU_NB; ++j) prow[j] = x[j];
+                prinv = best > 0.0 ? crecip(x[c]) : cmake(0.0, 0.0);
                 rows_out[(int64_t)blockIdx.x * LU_NB + c] = myrow;
+                s_win[c] = myrow;
+                if (is_final) {
+#pragma unroll
+                    for (int j = 0; j < LU_NB; ++j) fin.dblk[c * LU_NB + j] = x[j];
+                    if (best == 0.0) atomicCAS(fin.info, 0, (int)(fin.j + c + 1));
+                }
                 active = false;
             }
-            if (!any && tid == 0) rows_out[(int64_t)blockIdx.x * LU_NB + c] = -1;
+            if (!any && tid == 0) { rows_out[(int64_t)blockIdx.x * LU_NB + c] = -1; s_win[c] = -1; }
             __syncthreads();
             if (any && active && best > 0.0) {
-                const cplx l = cdiv(x[c], prow[c]);
+                const cplx l = cmul(x[c], prinv);
+                x[c] = l;  // multiplier: becomes part of the factored diagonal block if this row pivots later
 #pragma unroll
                 for (int j = c + 1; j < LU_NB; ++j) x[j] = cfma(cmake(-l.x, -l.y), prow[j], x[j]);
             }
         } else {
-            if (tid == 0) rows_out[(int64_t)blockIdx.x * LU_NB + c] = -1;
+            if (tid == 0) { rows_out[(int64_t)blockIdx.x * LU_NB + c] = -1; s_win[c] = -1; }
         }
     }
-}
-
-// Convert the ordered pivot-row list of a panel into LAPACK-style sequential swaps ipiv[j + c].
-__global__ void lu_pivots_kernel(const int32_t* __restrict__ cand, int64_t j, int w, int32_t* __restrict__ ipiv) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    int32_t piv[LU_NB];
-    for (int c = 0; c < w; ++c) {
-        int32_t loc = cand[c];
-        if (loc < 0) loc = (int32_t)(j + c);  // cannot happen for a square matrix; keep the row in place
-        // follow the earlier swaps of this panel
-        for (int q = 0; q < c; ++q) {
-            int32_t a = (int32_t)(j + q), b = piv[q];
-            if (loc == a) loc = b;
-            else if (loc == b) loc = a;
+    if (is_final) {
+        __syncthreads();
+        if (tid == 0) {
+            // ordered pivot rows -> sequential swaps (follow the earlier swaps of this panel)
+            int32_t piv[LU_NB];
+            for (int c = 0; c < w; ++c) {
+                int32_t loc = s_win[c];
+                if (loc < 0) loc = (int32_t)(fin.j + c);  // cannot happen for a square matrix; keep the row in place
+                for (int q = 0; q < c; ++q) {
+                    int32_t a0 = (int32_t)(fin.j + q), b0 = piv[q];
+                    if (loc == a0) loc = b0;
+                    else if (loc == b0) loc = a0;
+                }
+                piv[c] = loc;
+                fin.ipiv[fin.j + c] = loc;
+            }
         }
-        piv[c] = loc;
-        ipiv[j + c] = loc;
     }
 }
 
 // Apply the swaps of one panel to `ncols` contiguous columns of a row-major array (matrix or rhs).
+// With `dblk` (matrix only) the panel's own columns [j, j+w) of rows [j, j+w) then receive the factored diagonal
+// block produced by the last tournament round.
 __global__ void lu_swap_kernel(cplx* __restrict__ M, int64_t ld, int64_t ncols, const int32_t* __restrict__ ipiv,
-                               int64_t j, int w) {
+                               int64_t j, int w, const cplx* __restrict__ dblk) {
     int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncols) return;
     for (int q = 0; q < w; ++q) {
@@ -278,62 +296,32 @@ __global__ void lu_swap_kernel(cplx* __restrict__ M, int64_t ld, int64_t ncols, 
             M[b * ld + c] = va;
         }
     }
-}
-
-// Unpivoted LU of the w x w diagonal block (single CTA, 256 threads), in place.
-__global__ void __launch_bounds__(256) lu_diag_kernel(cplx* __restrict__ A, int64_t ld, int64_t j, int w,
-                                                      int32_t* __restrict__ info) {
-    __shared__ cplx t[LU_NB][LU_NB + 1];
-    const int tid = threadIdx.x;
-    for (int e = tid; e < w * w; e += 256) t[e / w][e % w] = A[(j + e / w) * ld + j + e % w];
-    __syncthreads();
-    for (int c = 0; c < w; ++c) {
-        cplx p = t[c][c];
-        if (p.x == 0.0 && p.y == 0.0) {
-            if (tid == 0) atomicCAS(info, 0, (int)(j + c + 1));
-            __syncthreads();
-            continue;
-        }
-        cplx ip = crecip(p);
-        __syncthreads();
-        for (int r = c + 1 + tid; r < w; r += 256) t[r][c] = cmul(t[r][c], ip);
-        __syncthreads();
-        int rem = w - c - 1;
-        for (int e = tid; e < rem * rem; e += 256) {
-            int r = c + 1 + e / rem, q = c + 1 + e % rem;
-            t[r][q] = cfma(cmake(-t[r][c].x, -t[r][c].y), t[c][q], t[r][q]);
-        }
-        __syncthreads();
-    }
-    for (int e = tid; e < w * w; e += 256) A[(j + e / w) * ld + j + e % w] = t[e / w][e % w];
+    if (dblk && c >= j && c < j + w)
+        for (int q = 0; q < w; ++q) M[(j + q) * ld + c] = dblk[q * LU_NB + (c - j)];
 }
 
 // L21 = A21 U11^{-1}: one row per thread (registers), U11 in shared memory.  Also emits the packed
 // GEMM image of the new L columns (rows below the diagonal block).
 __global__ void __launch_bounds__(LU_R) lu_l21_kernel(cplx* __restrict__ A, int64_t ld, int64_t N, int64_t j, int w) {
-    extern __shared__ __align__(16) unsigned char lu_dyn_smem[];
-    cplx (*tile)[LU_NB + 1] = reinterpret_cast<cplx (*)[LU_NB + 1]>(lu_dyn_smem);
     __shared__ cplx U[LU_NB][LU_NB + 1];
     __shared__ cplx rdiag[LU_NB];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const int64_t r0 = j + w + (int64_t)blockIdx.x * LU_R;
     for (int e = tid; e < LU_NB * LU_NB; e += LU_R) {
         int r = e / LU_NB, c = e % LU_NB;
         U[r][c] = (r < w && c < w && c >= r) ? A[(j + r) * ld + j + c] : cmake(0.0, 0.0);
     }
-    for (int rr = warp; rr < LU_R; rr += LU_R / 32) {
-        int64_t gr = r0 + rr;
-        tile[rr][lane] = (gr < N && lane < w) ? A[gr * ld + j + lane] : cmake(0.0, 0.0);
-    }
+    const int64_t myr = r0 + tid;
+    cplx* rowp = A + (myr < N ? myr : 0) * ld + j;
+    cplx x[LU_NB];
+#pragma unroll
+    for (int c = 0; c < LU_NB; ++c) x[c] = (myr < N && c < w) ? rowp[c] : cmake(0.0, 0.0);
     __syncthreads();
     if (tid < LU_NB) {
         cplx d = U[tid][tid];
         rdiag[tid] = (tid < w && (d.x != 0.0 || d.y != 0.0)) ? crecip(d) : cmake(0.0, 0.0);
     }
     __syncthreads();
-    cplx x[LU_NB];
-#pragma unroll
-    for (int c = 0; c < LU_NB; ++c) x[c] = tile[tid][c];
 #pragma unroll
     for (int c = 0; c < LU_NB; ++c) {
         // x[c] = (a[c] - sum_{q<c} x[q] U[q][c]) / U[c][c]
@@ -342,13 +330,10 @@ __global__ void __launch_bounds__(LU_R) lu_l21_kernel(cplx* __restrict__ A, int6
         for (int q = 0; q < c; ++q) s = cfma(cmake(-x[q].x, -x[q].y), U[q][c], s);
         x[c] = cmul(s, rdiag[c]);
     }
-    __syncthreads();
+    if (myr < N) {
 #pragma unroll
-    for (int c = 0; c < LU_NB; ++c) tile[tid][c] = x[c];
-    __syncthreads();
-    for (int rr = warp; rr < LU_R; rr += LU_R / 32) {
-        int64_t gr = r0 + rr;
-        if (gr < N && lane < w) A[gr * ld + j + lane] = tile[rr][lane];
+        for (int c = 0; c < LU_NB; ++c)
+            if (c < w) rowp[c] = x[c];
     }
 }
 
@@ -463,6 +448,7 @@ struct LuCtx {
     int32_t* ipiv;
     int32_t* info;
     int32_t* cand[2];
+    cplx* dblk;  // [LU_NB][LU_NB] factored diagonal block handed from the last tournament round to the swap kernel
     double* Lp;
     double* Up;
     int nks_total;      // LU_NBO / G_KC
@@ -474,6 +460,7 @@ struct LuCtx {
 struct LuWork {
     int32_t* cand0;
     int32_t* cand1;
+    cplx* dblk;
     double* Lp;
     double* Up;
     int64_t bytes;
@@ -486,6 +473,7 @@ static LuWork lu_carve(int64_t N, void* base) {
     int64_t ncand = cdiv64(N, LU_R) * LU_NB + LU_NB;
     w.cand0 = (int32_t*)take(ncand * 4);
     w.cand1 = (int32_t*)take(ncand * 4);
+    w.dblk = (cplx*)take((int64_t)LU_NB * LU_NB * sizeof(cplx));
     int64_t rtiles = cdiv64(N, G_TM) + 1, ctiles = cdiv64(N, G_TN) + 1;
     int nks = LU_NBO / G_KC;
     w.Lp = (double*)take(rtiles * nks * G_A_STAGE * 8);
@@ -555,28 +543,27 @@ static void lu_panel(LuCtx& x, int64_t j, int w) {
     int64_t nsets = cdiv64(M, LU_R);
     int cur = 0;
     bhs_prof_begin(BHS_PROF_LU_PANEL, x.st);
-    lu_select_kernel<<<(unsigned)nsets, LU_R, LU_TILE_SMEM, x.st>>>(x.A, x.ld, j, w, nullptr, 0, j, x.N, x.cand[cur]);
+    const SelectFinal fin{j, x.ipiv, x.info, x.dblk}, nofin{0, nullptr, nullptr, nullptr};
+    lu_select_kernel<<<(unsigned)nsets, LU_R, 0, x.st>>>(x.A, x.ld, j, w, nullptr, 0, j, x.N, x.cand[cur],
+                                                         nsets == 1 ? fin : nofin);
     LU_LAUNCH_CHECK(x);
     while (nsets > 1) {
         int64_t n_in = nsets * LU_NB;
         int64_t nsets2 = cdiv64(n_in, LU_R);
-        lu_select_kernel<<<(unsigned)nsets2, LU_R, LU_TILE_SMEM, x.st>>>(x.A, x.ld, j, w, x.cand[cur], n_in, 0, 0, x.cand[cur ^ 1]);
+        lu_select_kernel<<<(unsigned)nsets2, LU_R, 0, x.st>>>(x.A, x.ld, j, w, x.cand[cur], n_in, 0, 0, x.cand[cur ^ 1],
+                                                              nsets2 == 1 ? fin : nofin);
         LU_LAUNCH_CHECK(x);
         cur ^= 1;
         nsets = nsets2;
     }
-    lu_pivots_kernel<<<1, 32, 0, x.st>>>(x.cand[cur], j, w, x.ipiv);
-    LU_LAUNCH_CHECK(x);
-    lu_swap_kernel<<<(unsigned)cdiv64(x.N, 256), 256, 0, x.st>>>(x.A, x.ld, x.N, x.ipiv, j, w);
+    lu_swap_kernel<<<(unsigned)cdiv64(x.N, 256), 256, 0, x.st>>>(x.A, x.ld, x.N, x.ipiv, j, w, x.dblk);
     LU_LAUNCH_CHECK(x);
     if (x.rhs) {
-        lu_swap_kernel<<<(unsigned)cdiv64(x.nrhs, 32), 32, 0, x.st>>>(x.rhs, x.nrhs, x.nrhs, x.ipiv, j, w);
+        lu_swap_kernel<<<(unsigned)cdiv64(x.nrhs, 32), 32, 0, x.st>>>(x.rhs, x.nrhs, x.nrhs, x.ipiv, j, w, nullptr);
         LU_LAUNCH_CHECK(x);
     }
-    lu_diag_kernel<<<1, 256, 0, x.st>>>(x.A, x.ld, j, w, x.info);
-    LU_LAUNCH_CHECK(x);
     if (j + w < x.N) {
-        lu_l21_kernel<<<(unsigned)cdiv64(x.N - j - w, LU_R), LU_R, LU_TILE_SMEM, x.st>>>(x.A, x.ld, x.N, j, w);
+        lu_l21_kernel<<<(unsigned)cdiv64(x.N - j - w, LU_R), LU_R, 0, x.st>>>(x.A, x.ld, x.N, j, w);
         LU_LAUNCH_CHECK(x);
     }
     bhs_prof_end(BHS_PROF_LU_PANEL, 0.0, x.st);
@@ -615,8 +602,6 @@ static void lu_rec(LuCtx& x, int64_t j0, int w) {
 static int lu_factor(LuCtx& x) {
     cudaMemsetAsync(x.info, 0, sizeof(int32_t), x.st);
     cudaFuncSetAttribute(zgemm_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
-    cudaFuncSetAttribute(lu_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LU_TILE_SMEM);
-    cudaFuncSetAttribute(lu_l21_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LU_TILE_SMEM);
     for (int64_t J = 0; J < x.N; J += LU_NBO) {
         int w = (int)((x.N - J < LU_NBO) ? (x.N - J) : LU_NBO);
         x.J = J;
@@ -670,7 +655,7 @@ static int lu_setup(LuCtx& x, int64_t N, double* d_A, int64_t ld, double* d_rhs,
     if (N > 2000000000LL / LU_NB) return BHS_ERR_UNSUPPORTED;
     LuWork w = lu_carve(N, d_work);
     x.A = (cplx*)d_A; x.ld = ld; x.N = N; x.rhs = (cplx*)d_rhs; x.nrhs = nrhs;
-    x.ipiv = d_ipiv; x.info = d_info; x.cand[0] = w.cand0; x.cand[1] = w.cand1;
+    x.ipiv = d_ipiv; x.info = d_info; x.cand[0] = w.cand0; x.cand[1] = w.cand1; x.dblk = w.dblk;
     x.Lp = w.Lp; x.Up = w.Up; x.nks_total = LU_NBO / G_KC; x.J = 0;
     x.st = (cudaStream_t)stream; x.err = 0;
     return BHS_OK;
