@@ -150,13 +150,16 @@ struct SmArrA {
 };
 // hp[s][pair][n''] = i^{n''} h_{n''}(k_s |t_pair|), n'' < L2
 __global__ void pair_radial_kernel(int d, int L2, int n_store, int B, int nsys, const double* __restrict__ ks,
-                                   const double* __restrict__ dist, cplx* __restrict__ hp) {
+                                   const double* __restrict__ dist, cplx* __restrict__ hp, double* __restrict__ scratch) {
     extern __shared__ __align__(16) double sm[];
-    const int T = blockDim.x;
-    SmArrA hr{sm + threadIdx.x, T};
-    SmArrA hi{sm + (size_t)n_store * T + threadIdx.x, T};
+    // order sequences in shared memory, or (very high orders) in a global scratch: see ball_radial_kernel
+    const int T = scratch ? gridDim.x * blockDim.x : blockDim.x;
+    const int t = scratch ? blockIdx.x * blockDim.x + threadIdx.x : threadIdx.x;
+    double* base = scratch ? scratch : sm;
+    SmArrA hr{base + t, T};
+    SmArrA hi{base + (size_t)n_store * T + t, T};
     int64_t np = (int64_t)B * B, total = np * nsys;
-    for (int64_t i = (int64_t)blockIdx.x * T + threadIdx.x; i < total; i += (int64_t)gridDim.x * T) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int s = (int)(i / np);
         int64_t pr = i % np;
         if (pr / B == pr % B) {
@@ -199,6 +202,7 @@ __global__ void factors_kernel(int d, int L, int H, int B, int nsys, const doubl
 // ---- the assembly kernel --------------------------------------------------------------------------------
 struct AsmArgs {
     int B, H, H2, L2, nt_res;
+    int sy_global;             // 1: the S window does not fit in shared memory, gather from global (huge 2-D bands)
     const int32_t* n_unique;   // [1]   number of distinct translation vectors U
     const int32_t* grp_rep;    // [U]   representative pair of each
     const int32_t* grp_start;  // [U+1] member ranges
@@ -263,7 +267,8 @@ __global__ void __launch_bounds__(ASM_THREADS) assemble_kernel(AsmArgs a) {
         const cplx* y2 = a.Y2 + pr * a.H2 + hd.sy_lo;
         const cplx* hpw = a.hp + ((int64_t)sys * npairs + pr) * a.L2;
         const int32_t* dg = a.deg2 + hd.sy_lo;
-        for (int j = tid; j < hd.sy_cnt; j += ASM_THREADS) s_sy[j] = cmul(y2[j], hpw[dg[j]]);
+        if (!a.sy_global)
+            for (int j = tid; j < hd.sy_cnt; j += ASM_THREADS) s_sy[j] = cmul(y2[j], hpw[dg[j]]);
         __syncthreads();
         double ar0 = 0.0, ai0 = 0.0, ar1 = 0.0, ai1 = 0.0;
         for (int t0 = 0; t0 < nt; t0 += nt_res) {
@@ -281,7 +286,15 @@ __global__ void __launch_bounds__(ASM_THREADS) assemble_kernel(AsmArgs a) {
 #pragma unroll 4
             for (int t = 0; t < tn; ++t) {
                 const double cf0 = s_coef[t * BHS_TILE_E + e0], cf1 = s_coef[t * BHS_TILE_E + e1];
-                const cplx s0 = s_sy[s_idx[t * BHS_TILE_E + e0]], s1 = s_sy[s_idx[t * BHS_TILE_E + e1]];
+                const int i0 = s_idx[t * BHS_TILE_E + e0], i1 = s_idx[t * BHS_TILE_E + e1];
+                cplx s0, s1;
+                if (a.sy_global) {
+                    s0 = cmul(y2[i0], hpw[dg[i0]]);
+                    s1 = cmul(y2[i1], hpw[dg[i1]]);
+                } else {
+                    s0 = s_sy[i0];
+                    s1 = s_sy[i1];
+                }
                 ar0 = fma(cf0, s0.x, ar0); ai0 = fma(cf0, s0.y, ai0);
                 ar1 = fma(cf1, s1.x, ar1); ai1 = fma(cf1, s1.y, ai1);
             }
@@ -386,11 +399,19 @@ extern "C" int bhs_assemble(const bhs_plan_t* plan, int B, int nsys, const doubl
         int T = 64;
         while (T > 32 && (size_t)2 * n_store * T * sizeof(double) > 160 * 1024) T >>= 1;
         size_t smem = (size_t)2 * n_store * T * sizeof(double);
-        if (smem > 200 * 1024) return BHS_ERR_UNSUPPORTED;
-        cudaFuncSetAttribute(pair_radial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int64_t total = np * nsys, blocks = (total + T - 1) / T;
         if (blocks > 148 * 8) blocks = 148 * 8;
-        pair_radial_kernel<<<(unsigned)blocks, T, smem, st>>>(d, plan->L2, n_store, B, nsys, d_k, w.dist, w.hp);
+        if (smem > 200 * 1024) {
+            if (blocks > 32) blocks = 32;
+            double* scratch = nullptr;
+            if (cudaMallocAsync((void**)&scratch, (size_t)2 * n_store * blocks * T * sizeof(double), st) != cudaSuccess)
+                return BHS_ERR_ALLOC;
+            pair_radial_kernel<<<(unsigned)blocks, T, 0, st>>>(d, plan->L2, n_store, B, nsys, d_k, w.dist, w.hp, scratch);
+            cudaFreeAsync(scratch, st);
+        } else {
+            cudaFuncSetAttribute(pair_radial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            pair_radial_kernel<<<(unsigned)blocks, T, smem, st>>>(d, plan->L2, n_store, B, nsys, d_k, w.dist, w.hp, nullptr);
+        }
         BHS_CHECK_LAUNCH();
     }
     // the search is O(np^2) in the worst case (no duplicates): bounded by skipping it for more than 128 spheres
@@ -407,7 +428,11 @@ extern "C" int bhs_assemble(const bhs_plan_t* plan, int B, int nsys, const doubl
     // shared-memory budget: SY window (worst case H2 entries) + resident coefficient layers
     const size_t budget = 200 * 1024;
     size_t sy_bytes = ((size_t)plan->H2 * sizeof(cplx) + 127) & ~(size_t)127;
-    if (sy_bytes + (ASM_LAYER_COEF + ASM_LAYER_IDX) > budget) return BHS_ERR_UNSUPPORTED;
+    a.sy_global = 0;
+    if (sy_bytes + (ASM_LAYER_COEF + ASM_LAYER_IDX) > budget) {
+        a.sy_global = 1;
+        sy_bytes = 128;
+    }
     int nt_cap = (int)((budget - sy_bytes) / (ASM_LAYER_COEF + ASM_LAYER_IDX));
     a.nt_res = plan->max_nt < nt_cap ? (plan->max_nt > 0 ? plan->max_nt : 1) : nt_cap;
     size_t smem = (size_t)a.nt_res * (ASM_LAYER_COEF + ASM_LAYER_IDX) + sy_bytes;

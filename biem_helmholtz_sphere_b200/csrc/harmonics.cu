@@ -38,7 +38,8 @@ static int launch_harmonics(const bhs_plan* plan, int Lb, const int32_t* d_idx, 
                             int64_t npts, const double* d_scale, int conj_out, cplx* d_out, cudaStream_t st) {
     if (npts <= 0) return BHS_OK;
     HarmTables tb = harm_tables_of(plan);
-    const int warps = 4;
+    int warps = 4;
+    while (warps > 1 && harm_smem_bytes_per_warp(plan->d, Lb) * warps > 200 * 1024) warps >>= 1;
     size_t smem = harm_smem_bytes_per_warp(plan->d, Lb) * warps;
     if (smem > 200 * 1024) return BHS_ERR_UNSUPPORTED;
     cudaFuncSetAttribute(harmonics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -182,20 +182,59 @@ static int build_coupling(bhs_plan* p) {
         return acc;
     };
 
+    // 2-D (Graf): exactly one term per entry with a constant coefficient -- the tiles are filled directly (the
+    // generic path below would need H^2 small vectors, 47 M of them at the reference's largest run n_end = 3444).
+    // The i^{|m|+|m2|-|mp|} factor is split: i^{|m2|} into SY, i^{|m|} into the row and (-i)^{|mp|} into the column factor.
+    if (d == 2) {
+        const int Lb2 = p->L2;  // band-2 ordering: m2 = 0..Lb2-1, then -(Lb2-1)..-1
+        auto idx2 = [&](int m2) { return m2 >= 0 ? m2 : 2 * Lb2 - 1 + m2; };
+        p->coupling_terms = (int64_t)H * H;
+        p->tiles_r = (H + BHS_TILE_R - 1) / BHS_TILE_R;
+        p->tiles_c = (H + BHS_TILE_C - 1) / BHS_TILE_C;
+        const size_t ntile = (size_t)p->tiles_r * p->tiles_c;
+        p->h_tiles.assign(ntile, bhs_tile_hdr());
+        std::vector<double> coef(ntile * BHS_TILE_E, 0.0);
+        std::vector<uint16_t> cidx(ntile * BHS_TILE_E, 0);
+        p->max_nt = 1;
+        for (int tr = 0; tr < p->tiles_r; ++tr)
+            for (int tc = 0; tc < p->tiles_c; ++tc) {
+                const size_t ti = (size_t)tr * p->tiles_c + tc;
+                bhs_tile_hdr& hd = p->h_tiles[ti];
+                int lo = 1 << 30, hi = -1;
+                for (int r = 0; r < BHS_TILE_R; ++r)
+                    for (int c = 0; c < BHS_TILE_C; ++c) {
+                        int h = tr * BHS_TILE_R + r, hp = tc * BHS_TILE_C + c;
+                        if (h >= H || hp >= H) continue;
+                        int id = idx2(tab[hp] - tab[h]);
+                        lo = std::min(lo, id);
+                        hi = std::max(hi, id);
+                    }
+                if (hi < 0) { lo = 0; hi = 0; }
+                if (hi - lo > 65535) return BHS_ERR_UNSUPPORTED;
+                hd.nt = 1; hd.sy_lo = lo; hd.sy_cnt = hi - lo + 1; hd.pad = 0;
+                hd.coef_off = (int64_t)(ti * BHS_TILE_E);
+                hd.idx_off = (int64_t)(ti * BHS_TILE_E);
+                for (int r = 0; r < BHS_TILE_R; ++r)
+                    for (int c = 0; c < BHS_TILE_C; ++c) {
+                        int h = tr * BHS_TILE_R + r, hp = tc * BHS_TILE_C + c;
+                        if (h >= H || hp >= H) continue;
+                        const size_t o = ti * BHS_TILE_E + (size_t)r * BHS_TILE_C + c;
+                        coef[o] = (double)(cd * inv_s2pi);
+                        cidx[o] = (uint16_t)(idx2(tab[hp] - tab[h]) - lo);
+                    }
+            }
+        p->coupling_bytes = (int64_t)(coef.size() * sizeof(double) + cidx.size() * sizeof(uint16_t) +
+                                      p->h_tiles.size() * sizeof(bhs_tile_hdr));
+        int rc;
+        if ((rc = upload(&p->d_coef, coef))) return rc;
+        if ((rc = upload(&p->d_cidx, cidx))) return rc;
+        if ((rc = upload(&p->d_tiles, p->h_tiles))) return rc;
+        return BHS_OK;
+    }
     // terms[(h_row, h'_col)] : row = h (harmonic of ball b), col = h' (harmonic of ball b')
     std::vector<std::vector<Term>> terms((size_t)H * H);
     int64_t nterms = 0;
-    if (d == 2) {
-        for (int h = 0; h < H; ++h)
-            for (int hp = 0; hp < H; ++hp) {
-                int m = tab[h], mp = tab[hp];
-                int m2 = mp - m;
-                int idx = lookup2[{m2}];
-                // the i^{|m|+|m2|-|mp|} factor is split: i^{|m2|} into SY, i^{|m|} row, (-i)^{|mp|} col
-                terms[(size_t)h * H + hp].push_back({idx, (double)(cd * inv_s2pi)});
-                ++nterms;
-            }
-    } else if (d == 3) {
+    if (d == 3) {
         // memoise the theta integral over (n', |m'|, n, |m|, n'') -- |m''| is fixed by the sign pattern
         for (int h = 0; h < H; ++h) {
             int n = tab[h * 2], m = tab[h * 2 + 1];

@@ -11,14 +11,19 @@ struct StridedArr2 {
     __device__ __forceinline__ double& operator[](int n) const { return base[(size_t)n * stride]; }
 };
 
+// Order sequences live in shared memory (order-major, thread-minor); for very high orders (2-D runs with n_end in the
+// thousands) they do not fit and the caller passes a global scratch of 2 * n_store * (gridDim.x * blockDim.x) doubles.
 __global__ void ball_radial_kernel(int d, int L, int n_store, int B, int nsys, const double* __restrict__ radii,
-                                   const double* __restrict__ ks, double k_scalar, double4* __restrict__ out) {
+                                   const double* __restrict__ ks, double k_scalar, double4* __restrict__ out,
+                                   double* __restrict__ scratch) {
     extern __shared__ __align__(16) double sm[];
-    const int T = blockDim.x;
-    StridedArr2 aj{sm + threadIdx.x, T};
-    StridedArr2 ay{sm + (size_t)n_store * T + threadIdx.x, T};
+    const int T = scratch ? gridDim.x * blockDim.x : blockDim.x;
+    const int t = scratch ? blockIdx.x * blockDim.x + threadIdx.x : threadIdx.x;
+    double* base = scratch ? scratch : sm;
+    StridedArr2 aj{base + t, T};
+    StridedArr2 ay{base + (size_t)n_store * T + t, T};
     int64_t total = (int64_t)B * nsys;
-    for (int64_t i = (int64_t)blockIdx.x * T + threadIdx.x; i < total; i += (int64_t)gridDim.x * T) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int s = (int)(i / B), b = (int)(i % B);
         double x = (ks ? ks[s] : k_scalar) * radii[b];
         radial_sequence(d, x, L, aj, ay, true, true);
@@ -36,12 +41,22 @@ int launch_ball_radial(int d, int L, int B, int nsys, const double* d_radii, con
     int T = 64;
     while (T > 32 && (size_t)2 * n_store * T * sizeof(double) > 160 * 1024) T >>= 1;
     size_t smem = (size_t)2 * n_store * T * sizeof(double);
-    if (smem > 200 * 1024) return BHS_ERR_UNSUPPORTED;
-    cudaFuncSetAttribute(ball_radial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int64_t total = (int64_t)B * nsys;
     int64_t blocks = (total + T - 1) / T;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    ball_radial_kernel<<<(unsigned)blocks, T, smem, st>>>(d, L, n_store, B, nsys, d_radii, d_k, k_scalar, d_out);
+    if (smem > 200 * 1024) {
+        // high orders: sequences in a temporary global scratch (stream-ordered allocation, rare path)
+        if (blocks > 32) blocks = 32;
+        double* scratch = nullptr;
+        size_t bytes = (size_t)2 * n_store * blocks * T * sizeof(double);
+        if (cudaMallocAsync((void**)&scratch, bytes, st) != cudaSuccess) return BHS_ERR_ALLOC;
+        ball_radial_kernel<<<(unsigned)blocks, T, 0, st>>>(d, L, n_store, B, nsys, d_radii, d_k, k_scalar, d_out, scratch);
+        cudaFreeAsync(scratch, st);
+        BHS_CHECK_LAUNCH();
+        return BHS_OK;
+    }
+    cudaFuncSetAttribute(ball_radial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ball_radial_kernel<<<(unsigned)blocks, T, smem, st>>>(d, L, n_store, B, nsys, d_radii, d_k, k_scalar, d_out, nullptr);
     BHS_CHECK_LAUNCH();
     return BHS_OK;
 }

@@ -569,9 +569,11 @@ extern "C" int bhs_uscat(const bhs_plan_t* plan, int B, const double* d_centers,
                                                                             (cplx*)d_coef);
     BHS_CHECK_LAUNCH();
     a.coefg = (const cplx*)d_coef;
-    const int warps = 4;
+    int warps = 4;
     const int shift = (d & 1) ? (d - 3) / 2 : d / 2 - 1;
-    size_t smem = (harm_smem_bytes_per_warp(d, L) + (size_t)2 * (L + 2 + shift) * sizeof(double)) * warps;
+    const size_t per_warp = harm_smem_bytes_per_warp(d, L) + (size_t)2 * (L + 2 + shift) * sizeof(double);
+    while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
+    size_t smem = per_warp * warps;
     if (smem > 200 * 1024) return BHS_ERR_UNSUPPORTED;
     cudaFuncSetAttribute(uscat_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int64_t blocks = (P + warps - 1) / warps;
