@@ -60,7 +60,7 @@ __global__ void pair_rep_kernel(int d, int B, int dedupe, const double* __restri
     rep[i] = r;
 }
 // Single CTA: number the distinct translations and bucket the pairs.
-//   n_unique[0] = U;  grp_rep[u] = representative pair;  grp_start[u..u+1) -> members[] (pair ids)
+//   n_unique[0] = U;  grp_rep[u] = representative pair;  grp_start[u..u+1) -> members[] ((b << 16) | b')
 // uid[] and cursor[] are scratch of np ints each.
 __global__ void __launch_bounds__(1024) pair_group_kernel(int B, const int32_t* __restrict__ rep, int32_t* __restrict__ uid,
                                                           int32_t* __restrict__ cursor, int32_t* __restrict__ n_unique,
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(1024) pair_group_kernel(int B, const int32_t* 
     for (int i = tid; i < np; i += T)
         if (rep[i] >= 0) {
             const int u = uid[rep[i]];
-            members[grp_start[u] + atomicAdd(&cursor[u], 1)] = i;
+            members[grp_start[u] + atomicAdd(&cursor[u], 1)] = ((i / B) << 16) | (i % B);  // packed (b, b')
         }
 }
 
@@ -206,7 +206,7 @@ struct AsmArgs {
     const int32_t* n_unique;   // [1]   number of distinct translation vectors U
     const int32_t* grp_rep;    // [U]   representative pair of each
     const int32_t* grp_start;  // [U+1] member ranges
-    const int32_t* members;    // pair ids (b * B + b') bucketed by translation
+    const int32_t* members;    // pairs packed as (b << 16) | b', bucketed by translation
     const bhs_tile_hdr* tiles;
     const double* coef;
     const uint16_t* cidx;
@@ -301,16 +301,31 @@ __global__ void __launch_bounds__(ASM_THREADS) assemble_kernel(AsmArgs a) {
             if (!resident) __syncthreads();  // everyone done with the chunk before it is overwritten
         }
         const cplx raw0 = cmake(ar0, ai0), raw1 = cmake(ar1, ai1);
+        // Write phase: every pair that shares this translation gets the block, scaled by its own row / column factors.
+        // Members are handled four at a time with all factor loads issued before the first store (the loop is
+        // otherwise a chain of dependent global-memory latencies).
         const int q_end = a.grp_start[u + 1];
-        for (int q = a.grp_start[u]; q < q_end; ++q) {
-            const int prm = a.members[q];
-            const int b = prm / a.B, bp = prm % a.B;
-            if (ok0)
-                Asys[((int64_t)b * a.H + h0) * a.ld + (int64_t)bp * a.H + hp0] =
-                    cmul(cmul(raw0, rowf[(int64_t)b * a.H + h0]), colf[(int64_t)bp * a.H + hp0]);
-            if (ok1)
-                Asys[((int64_t)b * a.H + h1) * a.ld + (int64_t)bp * a.H + hp1] =
-                    cmul(cmul(raw1, rowf[(int64_t)b * a.H + h1]), colf[(int64_t)bp * a.H + hp1]);
+        for (int q0 = a.grp_start[u]; q0 < q_end; q0 += 4) {
+            int bb[4], bq[4];
+            cplx rf0[4], rf1[4], cf0[4], cf1[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int pk = (q0 + i < q_end) ? __ldg(a.members + q0 + i) : -1;
+                bb[i] = pk >> 16;
+                bq[i] = pk & 0xffff;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (bb[i] < 0) continue;
+                if (ok0) { rf0[i] = __ldg(rowf + (int64_t)bb[i] * a.H + h0); cf0[i] = __ldg(colf + (int64_t)bq[i] * a.H + hp0); }
+                if (ok1) { rf1[i] = __ldg(rowf + (int64_t)bb[i] * a.H + h1); cf1[i] = __ldg(colf + (int64_t)bq[i] * a.H + hp1); }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (bb[i] < 0) continue;
+                if (ok0) Asys[((int64_t)bb[i] * a.H + h0) * a.ld + (int64_t)bq[i] * a.H + hp0] = cmul(cmul(raw0, rf0[i]), cf0[i]);
+                if (ok1) Asys[((int64_t)bb[i] * a.H + h1) * a.ld + (int64_t)bq[i] * a.H + hp1] = cmul(cmul(raw1, rf1[i]), cf1[i]);
+            }
         }
         __syncthreads();  // s_sy reuse
     }
@@ -382,6 +397,7 @@ extern "C" int bhs_assemble(const bhs_plan_t* plan, int B, int nsys, const doubl
     if (!plan || B <= 0 || nsys <= 0 || !d_centers || !d_radii || !d_k || !d_A || !d_work) return BHS_ERR_INVALID;
     const int64_t N = (int64_t)B * plan->H;
     if (ld < N) return BHS_ERR_INVALID;
+    if (B > 32767) return BHS_ERR_UNSUPPORTED;  // pairs are packed as (b << 16) | b' in 32 bits
     cudaStream_t st = (cudaStream_t)stream;
     AsmWork w = carve(plan, B, nsys, d_work);
     bhs_prof_begin(BHS_PROF_ASM_PRE, st);
