@@ -10,6 +10,8 @@
 //   arithmetic through the real embedding  [ar ai] x [[br bi],[-bi br]], operands pre-packed by the
 //   triangular-solve kernels into the exact shared-memory image (padded, conflict-free) so that every
 //   pipeline stage is two 1-D TMA bulk copies (cp.async.bulk + mbarrier), 3 stages deep.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "prof.h"
 
@@ -602,9 +604,19 @@ static void lu_rec(LuCtx& x, int64_t j0, int w) {
 static int lu_factor(LuCtx& x) {
     cudaMemsetAsync(x.info, 0, sizeof(int32_t), x.st);
     cudaFuncSetAttribute(zgemm_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
+    // BHS_LU_GEMM_ONLY=1 (measurement aid, wrong results): issue only the trailing updates, to see how much of a
+    // sweep's time the DMMA kernel accounts for on its own
+    static const bool gemm_only = getenv("BHS_LU_GEMM_ONLY") != nullptr;
     for (int64_t J = 0; J < x.N; J += LU_NBO) {
         int w = (int)((x.N - J < LU_NBO) ? (x.N - J) : LU_NBO);
         x.J = J;
+        if (gemm_only) {
+            if (J + w < x.N) {
+                lu_pack_u(x, J, w, J + w, x.N);
+                lu_gemm(x, J + w, x.N, J + w, x.N, J, w);
+            }
+            continue;
+        }
         lu_rec(x, J, w);
         if (x.rhs) {
             // forward substitution of this block row: y_J = L11^{-1} rhs_J ; rhs_below -= L21 y_J
