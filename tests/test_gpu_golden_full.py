@@ -26,3 +26,27 @@ def test_golden_csv_replay():
     assert r["run"] >= 97 and r["outside_tolerance"] == 0, r
     full = gs.sweep(stride=1, max_n_end_2d=64, max_n_end_3d=16)["jascome_output.csv"]
     assert full["run"] == full["rows"] == 24 and full["outside_tolerance"] == 0, full
+
+
+def test_jascome_csv_writer_matches_reference_file(tmp_path):
+    """sweeps.jascome writes the reference's CSV format (cli.py:56-60,106-112); diff it against the golden file."""
+    import csv
+
+    from biem_helmholtz_sphere_b200 import sweeps
+    from golden_util import load
+
+    out = sweeps.jascome(str(tmp_path / "jascome_output.csv"), "a,ba,bba")
+    rows = list(csv.DictReader(open(out)))
+    ref_hdr = open(os.path.join(ROOT, "tests", "golden", "jascome_output.csv")).readline().strip()
+    assert open(out).readline().strip() == ref_hdr
+    assert [r["branching_types"] for r in rows] == ["bba"] * 9 + ["ba"] * 9 + ["a"] * 9  # reversed order, n_end 1..9
+    gold = {(r["branching_types"], r["n_end"]): r["uscat"] for r in load("jascome_output.csv")}
+    tol = {6: 5e-10, 7: 1e-9, 8: 2e-9, 9: 1e-7}
+    n = 0
+    for r in rows:
+        key = (r["branching_types"], int(r["n_end"]))
+        if key in gold:  # the reference's bba run stopped at n_end = 6
+            v = complex(r["uscat"])
+            assert abs(v - gold[key]) <= tol.get(key[1], 1e-10) * abs(gold[key]), key
+            n += 1
+    assert n == 24
