@@ -188,14 +188,28 @@ struct SelectFinal {
     cplx* dblk;
 };
 
+// 1 / p without the two divisions of Smith's algorithm when |p|^2 can neither overflow nor underflow
+__device__ __forceinline__ cplx crecip_fast(cplx p) {
+    const double s = fmax(fabs(p.x), fabs(p.y));
+    if (s > 1e-140 && s < 1e140) {
+        const double d = 1.0 / fma(p.x, p.x, p.y * p.y);
+        return cmake(p.x * d, -p.y * d);
+    }
+    return crecip(p);
+}
+
+// One elimination step costs ONE block barrier: every warp finds its own best row with three warp-wide reductions
+// (the magnitude's bit pattern is a monotone 64-bit key), that row's owner publishes the row and its reciprocal pivot in
+// the warp's slot of a double-buffered shared array, and after the barrier every thread picks the winning warp's slot.
 __global__ void __launch_bounds__(LU_R) lu_select_kernel(const cplx* __restrict__ A, int64_t ld, int64_t col0, int w,
                                                          const int32_t* __restrict__ rows_in, int64_t n_in,
                                                          int64_t row_begin, int64_t row_end,
                                                          int32_t* __restrict__ rows_out, SelectFinal fin) {
-    __shared__ cplx prow[LU_NB];
-    __shared__ cplx prinv;
-    __shared__ double wmag[LU_R / 32];
-    __shared__ int wlane[LU_R / 32];
+    constexpr int NW = LU_R / 32;
+    __shared__ cplx prow[2][NW][LU_NB];
+    __shared__ cplx prinv[2][NW];
+    __shared__ unsigned long long wkey[2][NW];
+    __shared__ int wlane[2][NW];
     __shared__ int32_t s_win[LU_NB];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool is_final = fin.ipiv != nullptr;
@@ -220,44 +234,52 @@ __global__ void __launch_bounds__(LU_R) lu_select_kernel(const cplx* __restrict_
 #pragma unroll
     for (int c = 0; c < LU_NB; ++c) {
         if (c < w) {
-            double mag = active ? fabs(x[c].x) + fabs(x[c].y) : -1.0;
-            int bl = lane;
-            double bm = mag;
+            const int buf = c & 1;
+            // key: 0 = no candidate, otherwise 1 + bits(|re| + |im|)  (monotone in the magnitude)
+            const double mag = fabs(x[c].x) + fabs(x[c].y);
+            const unsigned long long key = active ? (unsigned long long)__double_as_longlong(mag) + 1ULL : 0ULL;
+            const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+            const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+            const bool cand = hi == mhi;
+            const unsigned mlo = __reduce_max_sync(0xffffffffu, cand ? lo : 0u);
+            const unsigned vote = __ballot_sync(0xffffffffu, cand && lo == mlo);
+            const int bl = __ffs(vote) - 1;
+            if (lane == bl) {
+                wkey[buf][warp] = key;
+                wlane[buf][warp] = bl;
+                if (key) {
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                double om = __shfl_xor_sync(0xffffffffu, bm, o);
-                int ol = __shfl_xor_sync(0xffffffffu, bl, o);
-                if (om > bm || (om == bm && ol < bl)) { bm = om; bl = ol; }
+                    for (int j = c; j < LU_NB; ++j) prow[buf][warp][j] = x[j];
+                    prinv[buf][warp] = key > 1ULL ? crecip_fast(x[c]) : cmake(0.0, 0.0);
+                }
             }
-            if (lane == 0) { wmag[warp] = bm; wlane[warp] = bl; }
             __syncthreads();
             int bw = 0;
-            double best = wmag[0];
+            unsigned long long best = wkey[buf][0];
 #pragma unroll
-            for (int q = 1; q < LU_R / 32; ++q)
-                if (wmag[q] > best) { best = wmag[q]; bw = q; }
-            const int winner = bw * 32 + wlane[bw];
-            const bool any = best >= 0.0;  // at least one active row left
+            for (int q = 1; q < NW; ++q) {
+                const unsigned long long kq = wkey[buf][q];
+                if (kq > best) { best = kq; bw = q; }
+            }
+            const bool any = best != 0ULL;       // at least one active row left
+            const bool nonzero = best > 1ULL;    // its pivot entry is not exactly zero
+            const int winner = bw * 32 + wlane[buf][bw];
             if (any && tid == winner) {
-#pragma unroll
-                for (int j = c; j < LU_NB; ++j) prow[j] = x[j];
-                prinv = best > 0.0 ? crecip(x[c]) : cmake(0.0, 0.0);
                 rows_out[(int64_t)blockIdx.x * LU_NB + c] = myrow;
                 s_win[c] = myrow;
                 if (is_final) {
 #pragma unroll
                     for (int j = 0; j < LU_NB; ++j) fin.dblk[c * LU_NB + j] = x[j];
-                    if (best == 0.0) atomicCAS(fin.info, 0, (int)(fin.j + c + 1));
+                    if (!nonzero) atomicCAS(fin.info, 0, (int)(fin.j + c + 1));
                 }
                 active = false;
             }
             if (!any && tid == 0) { rows_out[(int64_t)blockIdx.x * LU_NB + c] = -1; s_win[c] = -1; }
-            __syncthreads();
-            if (any && active && best > 0.0) {
-                const cplx l = cmul(x[c], prinv);
+            if (any && active && nonzero) {
+                const cplx l = cmul(x[c], prinv[buf][bw]);
                 x[c] = l;  // multiplier: becomes part of the factored diagonal block if this row pivots later
 #pragma unroll
-                for (int j = c + 1; j < LU_NB; ++j) x[j] = cfma(cmake(-l.x, -l.y), prow[j], x[j]);
+                for (int j = c + 1; j < LU_NB; ++j) x[j] = cfma(cmake(-l.x, -l.y), prow[buf][bw][j], x[j]);
             }
         } else {
             if (tid == 0) { rows_out[(int64_t)blockIdx.x * LU_NB + c] = -1; s_win[c] = -1; }
