@@ -1,0 +1,99 @@
+"""Edge cases of the public API on the GPU path: empty point sets, n_end = 1, float32 inputs, CUDA-tensor inputs,
+points exactly on a centre / polar axis, uneven radii, and the expand_x switch."""
+import numpy as np
+import pytest
+
+from oracle import biem_oracle as bo
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def bhs():
+    import biem_helmholtz_sphere_b200 as m
+
+    return m
+
+
+def rel(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+
+
+@pytest.mark.parametrize("btype", ["a", "ba", "bba"])
+def test_empty_points_and_n_end_one(bhs, btype):
+    c = bhs.create_from_branching_types(btype)
+    d = c.c_ndim
+    cen = bo.grid_centers(0, d)
+    k = np.asarray(1.0)
+    uin = bhs.plane_wave(k=k, direction=np.eye(d)[0])[0]
+    calc = bhs.biem(c, uin=uin, k=k, n_end=1, centers=cen, radii=np.ones(2))
+    assert calc.density.shape == (2, 1)
+    ref = bo.biem(btype, uin=bo.plane_wave(k=1.0, direction=np.eye(d)[0])[0], k=1.0, n_end=1, centers=cen, radii=np.ones(2))
+    assert rel(calc.density, ref.density) < TOL
+    assert calc.uscat(np.zeros((d, 0))).shape == (0,)
+    assert calc.uscat(np.zeros((d, 0, 4))).shape == (0, 4)
+    assert calc.uscat(np.zeros((d, 0)), per_ball=True).shape == (0, 2)
+    assert abs(complex(calc.uscat(np.zeros(d))) - complex(ref.uscat(np.zeros(d)))) < TOL
+
+
+def test_float32_inputs_are_upcast_and_cuda_tensors_stay_on_device(bhs):
+    import torch
+
+    c = bhs.create_from_branching_types("ba")
+    cen64 = np.array([[0.0, 2.0, 0.0], [0.0, -2.0, 0.0]])
+    k = np.float32(1.5)
+    uin = bhs.plane_wave(k=np.asarray(k, dtype=np.float32), direction=np.array([1.0, 0.0, 0.0], dtype=np.float32))[0]
+    calc = bhs.biem(c, uin=uin, k=np.asarray(k), n_end=6, centers=cen64.astype(np.float32), radii=np.ones(2, np.float32))
+    assert calc.density.dtype == np.complex128
+    ref = bo.biem("ba", uin=bo.plane_wave(k=1.5, direction=np.array([1.0, 0, 0]))[0], k=1.5, n_end=6, centers=cen64, radii=np.ones(2))
+    assert rel(calc.density, ref.density) < TOL
+    dev = torch.device("cuda")
+    kt = torch.tensor(1.5, dtype=torch.float64, device=dev)
+    uin_t = bhs.plane_wave(k=kt, direction=torch.tensor([1.0, 0.0, 0.0], dtype=torch.float64, device=dev))[0]
+    calc_t = bhs.biem(c, uin=uin_t, k=kt, n_end=6, centers=torch.tensor(cen64, device=dev),
+                      radii=torch.ones(2, dtype=torch.float64, device=dev))
+    assert calc_t.density.is_cuda and calc_t.matrix.is_cuda and calc_t.centers.shape == (3, 2)
+    u = calc_t.uscat(torch.zeros(3, 5, dtype=torch.float64, device=dev))
+    assert u.is_cuda and u.shape == (5,)
+    assert rel(calc_t.density.cpu().numpy(), ref.density) < TOL
+
+
+def test_points_on_axes_and_centres_uneven_radii(bhs):
+    """Degenerate directions: on the polar axis of a ball (sin(theta) = 0) and outside-NaN logic at a ball's centre."""
+    c = bhs.create_from_branching_types("ba")
+    cen = np.array([[0.0, 2.0, 0.0], [0.0, -2.5, 0.0], [5.0, 0.0, 0.0]])
+    rad = np.array([1.0, 1.4, 0.3])
+    k = np.asarray(2.0)
+    calc = bhs.biem(c, uin=bhs.plane_wave(k=k, direction=np.array([0.0, 1.0, 0.0]))[0], k=k, n_end=12, centers=cen, radii=rad)
+    ref = bo.biem("ba", uin=bo.plane_wave(k=2.0, direction=np.array([0.0, 1.0, 0.0]))[0], k=2.0, n_end=12, centers=cen, radii=rad)
+    x = np.array([[3.0, 0.0, 0.0],     # on the polar (x0) axis of ball 2, between balls
+                  [-4.0, 2.0, 0.0],    # on the polar axis through ball 0's centre
+                  [0.0, 2.0, 0.0],     # centre of ball 0 -> NaN (inside)
+                  [0.0, -2.5, 1.4 + 1e-12],  # just outside ball 1
+                  [5.0, 0.0, 0.3 - 1e-12]]).T  # just inside ball 2 -> NaN
+    u = calc.uscat(x)
+    want = ref.uscat(x)
+    assert np.array_equal(np.isnan(u), np.isnan(want))
+    assert np.array_equal(np.isnan(u), [False, False, True, False, True])
+    ok = ~np.isnan(want)
+    assert rel(u[ok], want[ok]) < TOL
+
+
+def test_expand_x_false_matches_loop(bhs):
+    c = bhs.create_from_branching_types("a")
+    cen = np.array([[0.0, 2.0], [0.0, -2.0]])
+    ks = np.array([0.8, 1.9, 3.1])
+    uin = bhs.plane_wave(k=ks, direction=np.array([[1.0], [0.0]]))[0]
+    calc = bhs.biem(c, uin=uin, k=ks, n_end=9, centers=cen[None], radii=np.ones((1, 2)), eta=np.ones(3))
+    rng = np.random.default_rng(5)
+    x = rng.uniform(3.5, 6.0, size=(2, 7, 3))  # one point set per system
+    u = calc.uscat(x, expand_x=False)
+    assert u.shape == (7, 3)
+    ue = calc.uscat(x[:, :, 1])  # expand: same points for every system
+    assert ue.shape == (7, 3)
+    assert np.allclose(u[:, 1], ue[:, 1], rtol=1e-13, atol=0)
+    for i, k in enumerate(ks):
+        ref = bo.biem("a", uin=bo.plane_wave(k=k, direction=np.array([1.0, 0.0]))[0], k=k, n_end=9, centers=cen, radii=np.ones(2))
+        assert rel(u[:, i], ref.uscat(x[:, :, i])) < TOL
