@@ -530,10 +530,10 @@ static int launch_uscat3d(const UscatArgs& a, cudaStream_t st) {
 extern "C" int bhs_uscat(const bhs_plan_t* plan, int B, const double* d_centers, const double* d_radii, double k,
                          double eta, const double* d_density, const double* d_x, int64_t P, int flags, double* d_out,
                          void* d_work, void* stream) {
-    if (!plan || B <= 0 || !d_centers || !d_radii || !d_density || !d_x || !d_out || !d_work || P < 0)
-        return BHS_ERR_INVALID;
+    if (!plan || B <= 0 || P < 0) return BHS_ERR_INVALID;
+    if (P == 0) return BHS_OK;  // empty point set: nothing to do (the buffers of empty arrays may be null)
+    if (!d_centers || !d_radii || !d_density || !d_x || !d_out || !d_work) return BHS_ERR_INVALID;
     if (!(k > 0.0)) return BHS_ERR_UNSUPPORTED;
-    if (P == 0) return BHS_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const int d = plan->d, L = plan->n_end, H = plan->H;
     const int64_t npair = (int64_t)L * (L + 1) / 2;
