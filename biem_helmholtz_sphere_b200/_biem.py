@@ -12,7 +12,9 @@ Inputs may be NumPy arrays or torch tensors (any device); results come back in t
 
 Deliberate differences from the reference (documented in DESIGN.md):
 * float32 inputs are up-cast; outputs are always complex128 (north_star: complex128 only);
-* complex wavenumbers with a non-zero imaginary part raise ``NotImplementedError``;
+* complex wavenumbers (Im k != 0) are implemented for 3-D ('ba') -- h_n by complex upward recurrence from closed forms,
+  j_n by Miller's algorithm -- and raise ``NotImplementedError`` for 2-D / 4-D (cylindrical family) and in
+  ``point_source``;
 * leading batch axes of ``k`` WORK together with ``uin`` (the reference raises there); the
   semantics are "identical to a loop of scalar-k calls";
 * extra keyword ``keep_matrix`` (default True = reference behaviour) lets sweeps drop the N x N matrices.
@@ -77,12 +79,20 @@ def _t(a, dtype=None) -> torch.Tensor:
     return t
 
 
-def _real_k(k: torch.Tensor) -> torch.Tensor:
+def _split_k(k: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor | None]:
+    """(Re k, Im k) as float64 tensors; the imaginary part is None when it vanishes identically (real fast path)."""
     if k.is_complex():
         if bool(torch.any(k.imag != 0)):
-            raise NotImplementedError("complex wavenumbers (Im k != 0) are not implemented in the B200 path")
+            return k.real.to(F64), k.imag.to(F64)
         k = k.real
-    return k.to(F64)
+    return k.to(F64), None
+
+
+def _real_k(k: torch.Tensor) -> torch.Tensor:
+    kr, ki = _split_k(k)
+    if ki is not None:
+        raise NotImplementedError("complex wavenumbers (Im k != 0) are not implemented for this call")
+    return kr
 
 
 def harm_n_ndim_le(n_end: int, *, c_ndim: int) -> int:
@@ -204,7 +214,7 @@ def _check_biem_inputs(bt: str, centers, radii, k, eta, alpha, beta):
             stacklevel=3,
         )
     kr = kk.real if kk.is_complex() else kk
-    if bool(torch.any(et * kr < 0)):
+    if bool(torch.any(et * kr < 0)) or (kk.is_complex() and bool(torch.any(kk.imag < 0))):
         warnings.warn(
             "The solution may be incorrectif not (Im k >= 0 and eta Re k >= 0).", UserWarning, stacklevel=3
         )
@@ -229,7 +239,7 @@ def _check_biem_inputs(bt: str, centers, radii, k, eta, alpha, beta):
         ) from e
     if cen.shape[-1] != d:
         raise ValueError(f"The last dimension of centers must be c.c_ndim={d}, but got {cen.shape[-1]}")
-    return cen.to(F64), rad.to(F64), _real_k(kk), et, al, be
+    return cen.to(F64), rad.to(F64), kk, et, al, be
 
 
 # --------------------------------------------------------------------------------------------------
@@ -302,6 +312,8 @@ def point_source(*, k: Array, source: Array, n: int) -> tuple[Callable[[Array], 
     ns = _NS(k, source)
 
     def _hankel(z, d: int, derivative: bool):
+        if np.iscomplexobj(z) if not isinstance(z, torch.Tensor) else z.is_complex():
+            raise NotImplementedError("point_source with a complex wavenumber is not implemented in the B200 path")
         zt = _t(z, F64)
         return ns.out(_ops.bessel(d, 2, n, zt, derivative)[..., n])
 
@@ -329,6 +341,7 @@ class _Slot:
         self.stream = torch.cuda.Stream(device=dev)
         self.A = torch.empty((N, N), dtype=C128, device=dev)
         self.k = torch.zeros((1,), dtype=F64, device=dev)
+        self.k_im = torch.zeros((1,), dtype=F64, device=dev)
         self.eta = torch.ones((1,), dtype=F64, device=dev)
         self.rhs = torch.zeros((N,), dtype=C128, device=dev)
         self.bufs = _ops.SolveBuffers(N, 1)
@@ -345,8 +358,9 @@ class SweepEngine:
     issues one graph launch per system.  Nothing here synchronises with the host.
     """
 
-    def __init__(self, d: int, n_end: int, B: int, nslots: int = 3, use_graphs: bool = True):
+    def __init__(self, d: int, n_end: int, B: int, nslots: int = 3, use_graphs: bool = True, complex_k: bool = False):
         self.d, self.n_end, self.B = d, n_end, B
+        self.complex_k = complex_k
         self.plan = get_plan(d, n_end)
         self.N = B * self.plan.H
         dev = _dev()
@@ -358,7 +372,8 @@ class SweepEngine:
         self.use_graphs = use_graphs
 
     def _body(self, s: _Slot, solve: bool) -> None:
-        _ops.assemble(self.d, self.n_end, self.cen, self.rad, s.k, s.eta, self.al, self.be, out=s.A[None], work=s.work)
+        _ops.assemble(self.d, self.n_end, self.cen, self.rad, s.k, s.eta, self.al, self.be, out=s.A[None], work=s.work,
+                      k_im=s.k_im if self.complex_k else None)
         if solve:
             _ops.zgesv_(s.A, s.rhs, s.bufs)
 
@@ -368,8 +383,8 @@ class SweepEngine:
         self.al.copy_(al)
         self.be.copy_(be)
 
-    def run(self, ks, etas, f_hat, out_density, out_matrix=None) -> None:
-        """ks, etas: [K]; f_hat: [K, N]; out_density: [K, N]; out_matrix: [K, N, N] or None."""
+    def run(self, ks, etas, f_hat, out_density, out_matrix=None, kis=None) -> None:
+        """ks, etas (and kis = Im k for a complex_k engine): [K]; f_hat: [K, N]; out_density: [K, N]; out_matrix: [K, N, N] or None."""
         K = ks.shape[0]
         cur = torch.cuda.current_stream()
         ready = torch.cuda.Event()
@@ -380,12 +395,14 @@ class SweepEngine:
             s = self.slots[i % len(self.slots)]
             with torch.cuda.stream(s.stream):
                 s.k.copy_(ks[i : i + 1], non_blocking=True)
+                if self.complex_k:
+                    s.k_im.copy_(kis[i : i + 1], non_blocking=True)
                 s.eta.copy_(etas[i : i + 1], non_blocking=True)
                 s.rhs.copy_(f_hat[i], non_blocking=True)
                 if out_matrix is not None:
                     # the caller keeps the matrix: assemble, copy out, then factor the slot copy
                     _ops.assemble(self.d, self.n_end, self.cen, self.rad, s.k, s.eta, self.al, self.be, out=s.A[None],
-                                  work=s.work)
+                                  work=s.work, k_im=s.k_im if self.complex_k else None)
                     out_matrix[i].copy_(s.A, non_blocking=True)
                     _ops.zgesv_(s.A, s.rhs, s.bufs)
                 elif not self.use_graphs:
@@ -431,11 +448,11 @@ def _sweep_slots(N: int = 0) -> int:
     return slots
 
 
-def _get_engine(d: int, n_end: int, B: int, nslots: int) -> SweepEngine:
-    key = (torch.cuda.current_device(), d, n_end, B, nslots)
+def _get_engine(d: int, n_end: int, B: int, nslots: int, complex_k: bool = False) -> SweepEngine:
+    key = (torch.cuda.current_device(), d, n_end, B, nslots, complex_k)
     e = _engines.get(key)
     if e is None:
-        e = SweepEngine(d, n_end, B, nslots)
+        e = SweepEngine(d, n_end, B, nslots, complex_k=complex_k)
         _engines[key] = e
     return e
 
@@ -526,7 +543,12 @@ def biem(
     N = B * H
 
     shared_geom = all(int(np.prod(t.shape[:-1])) == 1 for t in (rad, al, be)) and int(np.prod(cen.shape[:-2])) == 1
+    k_user = kk
+    kk, kk_im = _split_k(kk)
+    if kk_im is not None and d != 3:
+        raise NotImplementedError("complex wavenumbers (Im k != 0) are implemented for 3-D ('ba') only")
     ks = kk.expand(batch_shape).reshape(K).contiguous()
+    kis = None if kk_im is None else kk_im.expand(batch_shape).reshape(K).contiguous()
     ets = et.expand(batch_shape).reshape(K).contiguous()
 
     def geom(i):
@@ -558,12 +580,14 @@ def biem(
         )
         if fused:
             c0, r0, a0, b0 = geom(0)
-            kin = _real_k(_t(tag["k"]))
+            kin, kin_im = _split_k(_t(tag["k"]))
             kin = kin.expand(batch_shape).reshape(K).contiguous() if nb else kin.reshape(1)
+            if kin_im is not None:
+                kin_im = kin_im.expand(batch_shape).reshape(K).contiguous() if nb else kin_im.reshape(1)
             dirv = _t(tag["direction"], F64).reshape(d).contiguous()
             f_hat = _ops.rhs_expand(d, n_end, centers=c0, radii=r0, k_in=kin, direction=dirv,
                                     alpha=a0 if uin is not None else torch.zeros_like(a0),
-                                    beta=b0 if uin_grad is not None else None)
+                                    beta=b0 if uin_grad is not None else None, k_in_im=kin_im)
         else:
             g = _boundary_data(bt, plan, ns, cen, rad, al, be, uin, uin_grad, batch_shape)
             f_hat = _ops.rhs_expand(d, n_end, g=g)  # [K, B, H]
@@ -578,21 +602,23 @@ def biem(
         for i in range(K) if not shared_geom else [None]:
             if i is None:
                 c0, r0, a0, b0 = geom(0)
-                diag = _ops.diag_coef(d, n_end, r0, ks, ets, a0, b0)  # [K, B, H]
+                diag = _ops.diag_coef(d, n_end, r0, ks, ets, a0, b0, k_im=kis)  # [K, B, H]
                 dens = f_hat / diag
             else:
                 c_i, r_i, a_i, b_i = geom(i)
-                dens.append(f_hat[i] / _ops.diag_coef(d, n_end, r_i, ks[i : i + 1], ets[i : i + 1], a_i, b_i)[0])
+                dens.append(f_hat[i] / _ops.diag_coef(d, n_end, r_i, ks[i : i + 1], ets[i : i + 1], a_i, b_i,
+                                                      k_im=None if kis is None else kis[i : i + 1])[0])
         density_t = dens if isinstance(dens, torch.Tensor) else torch.stack(dens)
     else:
         if f_hat is None:
             # matrix only (_biem.py:596-597,794-795)
             if shared_geom:
                 c0, r0, a0, b0 = geom(0)
-                matrix_t = _ops.assemble(d, n_end, c0, r0, ks, ets, a0, b0)
+                matrix_t = _ops.assemble(d, n_end, c0, r0, ks, ets, a0, b0, k_im=kis)
             else:
                 matrix_t = torch.stack([
-                    _ops.assemble(d, n_end, *geom(i)[:2], ks[i : i + 1], ets[i : i + 1], *geom(i)[2:])[0] for i in range(K)
+                    _ops.assemble(d, n_end, *geom(i)[:2], ks[i : i + 1], ets[i : i + 1], *geom(i)[2:],
+                                  k_im=None if kis is None else kis[i : i + 1])[0] for i in range(K)
                 ])
         else:
             density_t = torch.empty((K, N), dtype=C128, device=_dev())
@@ -600,15 +626,16 @@ def biem(
             rhs = f_hat.reshape(K, N)
             if shared_geom:
                 nslots = 1 if (K == 1 or N > 12000) else min(_sweep_slots(N), K)
-                eng = _get_engine(d, n_end, B, nslots)
+                eng = _get_engine(d, n_end, B, nslots, complex_k=kis is not None)
                 eng.set_geometry(*geom(0))
-                eng.run(ks, ets, rhs, density_t, matrix_t)
+                eng.run(ks, ets, rhs, density_t, matrix_t, kis=kis)
             else:
-                eng = _get_engine(d, n_end, B, 1)
+                eng = _get_engine(d, n_end, B, 1, complex_k=kis is not None)
                 for i in range(K):
                     eng.set_geometry(*geom(i))
                     eng.run(ks[i : i + 1], ets[i : i + 1], rhs[i : i + 1], density_t[i : i + 1],
-                            None if matrix_t is None else matrix_t[i : i + 1])
+                            None if matrix_t is None else matrix_t[i : i + 1],
+                            kis=None if kis is None else kis[i : i + 1])
 
     # ---- packaging (user namespace) ---------------------------------------------------------------
     density = None if density_t is None else ns.out(density_t.reshape(batch_shape + (B, H)))
@@ -627,11 +654,11 @@ def biem(
     cen_store = ns.out(torch.movedim(cen, -1, 0))  # [v, ..., B]  (_biem.py:588)
     dev_state = {
         "bt": bt, "batch_shape": batch_shape, "K": K, "B": B, "ks": ks, "etas": ets,
-        "ks_host": ks.tolist(), "etas_host": ets.tolist(),
+        "ks_host": ks.tolist() if kis is None else torch.complex(ks, kis).tolist(), "etas_host": ets.tolist(),
         "cen": cen, "rad": rad, "density": density_t, "geom_shared": shared_geom,
     }
     return BIEMResultCalculator(
-        c=c, centers=cen_store, radii=ns.out(rad), k=ns.out(kk), n_end=n_end, eta=ns.out(et), kind=kind,
+        c=c, centers=cen_store, radii=ns.out(rad), k=ns.out(k_user), n_end=n_end, eta=ns.out(et), kind=kind,
         uin=uin_wrapped, density=density, matrix=matrix, dev_state=dev_state,
     )
 
@@ -652,7 +679,7 @@ def biem_u(res: Any, x: Array, /, far_field: bool = False, per_ball: bool = Fals
     st = getattr(res, "_dev_state", None) or {}
     if not st:
         # a result record built by hand (or by another implementation): move its fields to the device
-        kk = _real_k(_t(res.k))
+        kk, kk_im = _split_k(_t(res.k))
         cen = torch.movedim(_t(res.centers, F64), 0, -1)
         rad = _t(res.radii, F64)
         et = _t(res.eta, F64)
@@ -662,7 +689,10 @@ def biem_u(res: Any, x: Array, /, far_field: bool = False, per_ball: bool = Fals
         B = dens.shape[-2]
         st = {
             "batch_shape": batch_shape, "K": K, "B": B,
-            "ks": kk.expand(batch_shape).reshape(K), "etas": et.expand(batch_shape).reshape(K) if et.numel() > 1 else et.reshape(1).expand(K),
+            "ks": kk.expand(batch_shape).reshape(K),
+            "ks_host": (kk.expand(batch_shape).reshape(K).tolist() if kk_im is None else
+                        torch.complex(kk, kk_im).expand(batch_shape).reshape(K).tolist()),
+            "etas": et.expand(batch_shape).reshape(K) if et.numel() > 1 else et.reshape(1).expand(K),
             "cen": cen, "rad": rad, "density": dens.reshape(K, -1),
         }
     batch_shape, K, B = st["batch_shape"], st["K"], st["B"]

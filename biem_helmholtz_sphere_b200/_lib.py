@@ -30,10 +30,10 @@ SIGNATURES = {
     "bhs_plan_coupling_stats": (i32, [vp, C.POINTER(i64), C.POINTER(i64)]),
     "bhs_bessel": (i32, [i32, i32, i32, i32, vp, i64, vp, vp]),
     "bhs_harmonics": (i32, [vp, i32, vp, i64, vp, vp]),
-    "bhs_rhs_expand": (i32, [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "bhs_rhs_expand": (i32, [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "bhs_assemble_workspace": (i64, [vp, i32, i32]),
-    "bhs_assemble": (i32, [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp, vp]),
-    "bhs_diag_coef": (i32, [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
+    "bhs_assemble": (i32, [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp, vp]),
+    "bhs_diag_coef": (i32, [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "bhs_zgesv_workspace": (i64, [i64, i32]),
     "bhs_zgesv": (i32, [i64, i32, vp, i64, vp, vp, vp, vp, vp]),
     "bhs_zgetrf": (i32, [i64, vp, i64, vp, vp, vp, vp]),
@@ -41,7 +41,7 @@ SIGNATURES = {
     "bhs_zgemm_workspace": (i64, [i64, i64, i64]),
     "bhs_zgemm_sub": (i32, [i64, i64, i64, vp, i64, vp, i64, vp, i64, vp, vp]),
     "bhs_uscat_workspace": (i64, [vp, i32]),
-    "bhs_uscat": (i32, [vp, i32, vp, vp, f64, f64, vp, vp, i64, i32, vp, vp, vp]),
+    "bhs_uscat": (i32, [vp, i32, vp, vp, f64, f64, f64, vp, vp, i64, i32, vp, vp, vp]),
     "bhs_fp64_peak": (i32, [i32, i32, C.POINTER(f64)]),
     "bhs_launch_count": (i64, [i32]),
     "bhs_profile": (i32, [i32]),

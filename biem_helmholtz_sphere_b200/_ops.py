@@ -56,8 +56,8 @@ def harmonics(d: int, n_end: int, xyz, double_band: bool = False) -> torch.Tenso
 
 
 def rhs_expand(d: int, n_end: int, *, g=None, centers=None, radii=None, k_in=None, direction=None, alpha=None,
-               beta=None, B: int | None = None) -> torch.Tensor:
-    """f_hat [nsys, B, H]; either sampled boundary data g [nsys, Q, B] or a fused plane wave."""
+               beta=None, B: int | None = None, k_in_im=None) -> torch.Tensor:
+    """f_hat [nsys, B, H]; either sampled boundary data g [nsys, Q, B] or a fused plane wave exp(i (k_in + i k_in_im) d.x)."""
     plan = get_plan(d, n_end)
     if g is not None:
         gt = _c128(g)
@@ -65,21 +65,23 @@ def rhs_expand(d: int, n_end: int, *, g=None, centers=None, radii=None, k_in=Non
         if Q != plan.Q:
             raise ValueError(f"g must have {plan.Q} quadrature rows, got {Q}")
         out = torch.empty((nsys, B, plan.H), dtype=C128, device=gt.device)
-        check(load().bhs_rhs_expand(plan.handle, B, nsys, ptr(gt), None, None, None, None, None, None, ptr(out),
+        check(load().bhs_rhs_expand(plan.handle, B, nsys, ptr(gt), None, None, None, None, None, None, None, ptr(out),
                                     stream_ptr()), "bhs_rhs_expand")
         return out
     cen, rad, kk, dr = _f64(centers), _f64(radii), _f64(k_in).reshape(-1), _f64(direction)
     B = rad.shape[0]
     al = None if alpha is None else _c128(alpha)
     be = None if beta is None else _c128(beta)
+    kim = None if k_in_im is None else _f64(k_in_im).reshape(-1)
     out = torch.empty((kk.numel(), B, plan.H), dtype=C128, device=cen.device)
-    check(load().bhs_rhs_expand(plan.handle, B, kk.numel(), None, ptr(cen), ptr(rad), ptr(kk), ptr(dr), ptr(al), ptr(be),
-                                ptr(out), stream_ptr()), "bhs_rhs_expand")
+    check(load().bhs_rhs_expand(plan.handle, B, kk.numel(), None, ptr(cen), ptr(rad), ptr(kk), ptr(kim), ptr(dr), ptr(al),
+                                ptr(be), ptr(out), stream_ptr()), "bhs_rhs_expand")
     return out
 
 
-def assemble(d: int, n_end: int, centers, radii, k, eta=None, alpha=None, beta=None, out=None, work=None) -> torch.Tensor:
-    """A [nsys, N, N] row-major   (bhs_assemble)."""
+def assemble(d: int, n_end: int, centers, radii, k, eta=None, alpha=None, beta=None, out=None, work=None,
+             k_im=None) -> torch.Tensor:
+    """A [nsys, N, N] row-major   (bhs_assemble); wavenumbers k + i k_im (k_im None = real)."""
     plan = get_plan(d, n_end)
     cen, rad, kk = _f64(centers), _f64(radii), _f64(k).reshape(-1)
     B = rad.shape[0]
@@ -92,12 +94,13 @@ def assemble(d: int, n_end: int, centers, radii, k, eta=None, alpha=None, beta=N
         out = torch.empty((nsys, N, N), dtype=C128, device=cen.device)
     if work is None:
         work = _work(load().bhs_assemble_workspace(plan.handle, B, nsys))
-    check(load().bhs_assemble(plan.handle, B, nsys, ptr(cen), ptr(rad), ptr(kk), ptr(et), ptr(al), ptr(be), ptr(out),
-                              N, N * N, ptr(work), stream_ptr()), "bhs_assemble")
+    kim = None if k_im is None else _f64(k_im).reshape(-1)
+    check(load().bhs_assemble(plan.handle, B, nsys, ptr(cen), ptr(rad), ptr(kk), ptr(kim), ptr(et), ptr(al), ptr(be),
+                              ptr(out), N, N * N, ptr(work), stream_ptr()), "bhs_assemble")
     return out
 
 
-def diag_coef(d: int, n_end: int, radii, k, eta=None, alpha=None, beta=None) -> torch.Tensor:
+def diag_coef(d: int, n_end: int, radii, k, eta=None, alpha=None, beta=None, k_im=None) -> torch.Tensor:
     plan = get_plan(d, n_end)
     rad, kk = _f64(radii), _f64(k).reshape(-1)
     B = rad.shape[0]
@@ -105,8 +108,9 @@ def diag_coef(d: int, n_end: int, radii, k, eta=None, alpha=None, beta=None) -> 
     al = None if alpha is None else _c128(alpha)
     be = None if beta is None else _c128(beta)
     out = torch.empty((kk.numel(), B, plan.H), dtype=C128, device=rad.device)
-    check(load().bhs_diag_coef(plan.handle, B, kk.numel(), ptr(rad), ptr(kk), ptr(et), ptr(al), ptr(be), ptr(out),
-                               stream_ptr()), "bhs_diag_coef")
+    kim = None if k_im is None else _f64(k_im).reshape(-1)
+    check(load().bhs_diag_coef(plan.handle, B, kk.numel(), ptr(rad), ptr(kk), ptr(kim), ptr(et), ptr(al), ptr(be),
+                               ptr(out), stream_ptr()), "bhs_diag_coef")
     return out
 
 
@@ -163,9 +167,9 @@ def zgemm_sub_(Cm: torch.Tensor, A: torch.Tensor, Bm: torch.Tensor, work=None):
     return Cm
 
 
-def uscat(d: int, n_end: int, centers, radii, k: float, eta: float, density, x, *, far_field=False, per_ball=False,
-          inner=False, work=None) -> torch.Tensor:
-    """u_s at x [d, P] -> [P] (or [P, B])   (bhs_uscat)."""
+def uscat(d: int, n_end: int, centers, radii, k: float | complex, eta: float, density, x, *, far_field=False,
+          per_ball=False, inner=False, work=None) -> torch.Tensor:
+    """u_s at x [d, P] -> [P] (or [P, B])   (bhs_uscat); k may be complex (3-D only)."""
     plan = get_plan(d, n_end)
     cen, rad, den, xt = _f64(centers), _f64(radii), _c128(density), _f64(x)
     B = rad.shape[0]
@@ -175,7 +179,8 @@ def uscat(d: int, n_end: int, centers, radii, k: float, eta: float, density, x, 
     out = torch.empty((P, B) if per_ball else (P,), dtype=C128, device=xt.device)
     if work is None:
         work = _work(load().bhs_uscat_workspace(plan.handle, B))
-    check(load().bhs_uscat(plan.handle, B, ptr(cen), ptr(rad), float(k), float(eta), ptr(den), ptr(xt), P, flags,
+    kc = complex(k)
+    check(load().bhs_uscat(plan.handle, B, ptr(cen), ptr(rad), kc.real, kc.imag, float(eta), ptr(den), ptr(xt), P, flags,
                            ptr(out), ptr(work), stream_ptr()), "bhs_uscat")
     return out
 

@@ -199,6 +199,60 @@ __global__ void factors_kernel(int d, int L, int H, int B, int nsys, const doubl
     if (diag) diag[i] = cmul(sd, sing);
 }
 
+// ---- complex wavenumber variants (3-D): same outputs, complex arguments -----------------------------------------
+struct SmArrZ {
+    cplx* p;
+    int stride;
+    __device__ __forceinline__ cplx& operator[](int n) const { return p[(size_t)n * stride]; }
+};
+__global__ void pair_radial_z_kernel(int L2, int n_store, int B, int nsys, const double* __restrict__ kr,
+                                     const double* __restrict__ ki, const double* __restrict__ dist,
+                                     cplx* __restrict__ hp) {
+    extern __shared__ __align__(16) cplx smz[];
+    const int T = blockDim.x;
+    SmArrZ ah{smz + threadIdx.x, T};
+    int64_t np = (int64_t)B * B, total = np * nsys;
+    for (int64_t i = (int64_t)blockIdx.x * T + threadIdx.x; i < total; i += (int64_t)gridDim.x * T) {
+        int s = (int)(i / np);
+        int64_t pr = i % np;
+        if (pr / B == pr % B) {
+            for (int n = 0; n < L2; ++n) hp[i * L2 + n] = cmake(0.0, 0.0);
+            continue;
+        }
+        const double r = dist[pr];
+        sph_sequence_z(cmake(kr[s] * r, ki[s] * r), L2 - 1, ah, ah, false, true);
+        for (int n = 0; n < L2; ++n) hp[i * L2 + n] = cmul_ipow(ah[n], n);
+    }
+    (void)n_store;
+}
+
+__global__ void factors_z_kernel(int d, int L, int H, int B, int nsys, const double* __restrict__ radii,
+                                 const double* __restrict__ kr, const double* __restrict__ ki,
+                                 const double* __restrict__ etas, const cplx* __restrict__ alpha,
+                                 const cplx* __restrict__ beta, const cplx* __restrict__ radz,
+                                 const int32_t* __restrict__ deg, cplx* __restrict__ rowf, cplx* __restrict__ colf,
+                                 cplx* __restrict__ diag) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t total = (int64_t)nsys * B * H;
+    if (i >= total) return;
+    int h = (int)(i % H);
+    int b = (int)((i / H) % B);
+    int s = (int)(i / ((int64_t)H * B));
+    int n = deg[h];
+    const cplx k = cmake(kr[s], ki[s]);
+    const double eta = etas ? etas[s] : 1.0;
+    const cplx* r = radz + (((int64_t)s * B + b) * L + n) * 4;  // j, j', h, h'
+    cplx al = alpha ? alpha[b] : cmake(1.0, 0.0);
+    cplx be = beta ? beta[b] : cmake(0.0, 0.0);
+    cplx bek = cmul(be, k);
+    cplx reg = cadd(cmul(al, r[0]), cmul(bek, r[1]));
+    cplx sing = cadd(cmul(al, r[2]), cmul(bek, r[3]));
+    cplx sd = sd_coef_z(d, k, eta, radii[b], r[0], r[1]);
+    if (rowf) rowf[i] = cmul_ipow(reg, n);
+    if (colf) colf[i] = cmul_ipow(sd, -n);
+    if (diag) diag[i] = cmul(sd, sing);
+}
+
 // ---- the assembly kernel --------------------------------------------------------------------------------
 struct AsmArgs {
     int B, H, H2, L2, nt_res;
@@ -351,7 +405,7 @@ static AsmWork carve(const bhs_plan* p, int B, int nsys, void* base) {
     unsigned char* c = (unsigned char*)base;
     int64_t np = (int64_t)B * B, off = 0;
     auto take = [&](int64_t bytes) { unsigned char* r = c + off; off += al256(bytes); return r; };
-    w.rad = (double4*)take((int64_t)nsys * B * p->n_end * sizeof(double4));
+    w.rad = (double4*)take((int64_t)nsys * B * p->n_end * 4 * sizeof(cplx));  // (j, j', y, y') real or (j, j', h, h') complex
     w.tv = (double*)take(np * p->d * sizeof(double));
     w.dist = (double*)take(np * sizeof(double));
     w.Y2 = (cplx*)take(np * p->H2 * sizeof(cplx));
@@ -376,11 +430,22 @@ extern "C" int64_t bhs_assemble_workspace(const bhs_plan_t* plan, int B, int nsy
 }
 
 static int run_factors(const bhs_plan* p, int B, int nsys, const double* d_radii, const double* d_k,
-                       const double* d_eta, const double* d_alpha, const double* d_beta, AsmWork& w, bool only_diag,
-                       cudaStream_t st) {
+                       const double* d_k_im, const double* d_eta, const double* d_alpha, const double* d_beta, AsmWork& w,
+                       bool only_diag, cudaStream_t st) {
+    int64_t tot = (int64_t)nsys * B * p->H;
+    if (d_k_im) {
+        int rc = launch_ball_radial_z(p->d, p->n_end, B, nsys, d_radii, d_k, d_k_im, 0.0, 0.0, (cplx*)w.rad, st);
+        if (rc) return rc;
+        factors_z_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(p->d, p->n_end, p->H, B, nsys, d_radii, d_k, d_k_im,
+                                                                       d_eta, (const cplx*)d_alpha, (const cplx*)d_beta,
+                                                                       (const cplx*)w.rad, p->d_deg,
+                                                                       only_diag ? nullptr : w.rowf,
+                                                                       only_diag ? nullptr : w.colf, w.diag);
+        BHS_CHECK_LAUNCH();
+        return BHS_OK;
+    }
     int rc = launch_ball_radial(p->d, p->n_end, B, nsys, d_radii, d_k, 0.0, w.rad, st);
     if (rc) return rc;
-    int64_t tot = (int64_t)nsys * B * p->H;
     factors_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(p->d, p->n_end, p->H, B, nsys, d_radii, d_k, d_eta,
                                                                  (const cplx*)d_alpha, (const cplx*)d_beta, w.rad,
                                                                  p->d_deg, only_diag ? nullptr : w.rowf,
@@ -392,8 +457,9 @@ static int run_factors(const bhs_plan* p, int B, int nsys, const double* d_radii
 int bhs_launch_harmonics_band2(const bhs_plan* plan, const double* d_xyz, int64_t npts, cplx* d_out, cudaStream_t st);
 
 extern "C" int bhs_assemble(const bhs_plan_t* plan, int B, int nsys, const double* d_centers, const double* d_radii,
-                            const double* d_k, const double* d_eta, const double* d_alpha, const double* d_beta,
-                            double* d_A, int64_t ld, int64_t sys_stride, void* d_work, void* stream) {
+                            const double* d_k, const double* d_k_im, const double* d_eta, const double* d_alpha,
+                            const double* d_beta, double* d_A, int64_t ld, int64_t sys_stride, void* d_work,
+                            void* stream) {
     if (!plan || B <= 0 || nsys <= 0 || !d_centers || !d_radii || !d_k || !d_A || !d_work) return BHS_ERR_INVALID;
     const int64_t N = (int64_t)B * plan->H;
     if (ld < N) return BHS_ERR_INVALID;
@@ -401,7 +467,8 @@ extern "C" int bhs_assemble(const bhs_plan_t* plan, int B, int nsys, const doubl
     cudaStream_t st = (cudaStream_t)stream;
     AsmWork w = carve(plan, B, nsys, d_work);
     bhs_prof_begin(BHS_PROF_ASM_PRE, st);
-    int rc = run_factors(plan, B, nsys, d_radii, d_k, d_eta, d_alpha, d_beta, w, false, st);
+    if (d_k_im && plan->d != 3) return BHS_ERR_UNSUPPORTED;  // complex wavenumbers: spherical family only
+    int rc = run_factors(plan, B, nsys, d_radii, d_k, d_k_im, d_eta, d_alpha, d_beta, w, false, st);
     if (rc) return rc;
     const int64_t np = (int64_t)B * B;
     pair_vectors_kernel<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(plan->d, B, d_centers, w.tv, w.dist);
@@ -417,7 +484,17 @@ extern "C" int bhs_assemble(const bhs_plan_t* plan, int B, int nsys, const doubl
         size_t smem = (size_t)2 * n_store * T * sizeof(double);
         int64_t total = np * nsys, blocks = (total + T - 1) / T;
         if (blocks > 148 * 8) blocks = 148 * 8;
-        if (smem > 200 * 1024) {
+        if (d_k_im) {
+            int Tz = 64;
+            const int ns = plan->L2 + 1;
+            while (Tz > 32 && (size_t)ns * Tz * sizeof(cplx) > 160 * 1024) Tz >>= 1;
+            size_t smz = (size_t)ns * Tz * sizeof(cplx);
+            if (smz > 200 * 1024) return BHS_ERR_UNSUPPORTED;
+            cudaFuncSetAttribute(pair_radial_z_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smz);
+            int64_t bz = (total + Tz - 1) / Tz;
+            if (bz > 148 * 8) bz = 148 * 8;
+            pair_radial_z_kernel<<<(unsigned)bz, Tz, smz, st>>>(plan->L2, ns, B, nsys, d_k, d_k_im, w.dist, w.hp);
+        } else if (smem > 200 * 1024) {
             if (blocks > 32) blocks = 32;
             double* scratch = nullptr;
             if (cudaMallocAsync((void**)&scratch, (size_t)2 * n_store * blocks * T * sizeof(double), st) != cudaSuccess)
@@ -478,17 +555,18 @@ extern "C" int bhs_assemble(const bhs_plan_t* plan, int B, int nsys, const doubl
 }
 
 extern "C" int bhs_diag_coef(const bhs_plan_t* plan, int B, int nsys, const double* d_radii, const double* d_k,
-                             const double* d_eta, const double* d_alpha, const double* d_beta, double* d_out,
-                             void* stream) {
+                             const double* d_k_im, const double* d_eta, const double* d_alpha, const double* d_beta,
+                             double* d_out, void* stream) {
     if (!plan || B <= 0 || nsys <= 0 || !d_radii || !d_k || !d_out) return BHS_ERR_INVALID;
     // needs only the radial table: carve it out of a temporary allocation
     cudaStream_t st = (cudaStream_t)stream;
     double4* rad = nullptr;
-    if (cudaMallocAsync((void**)&rad, (size_t)nsys * B * plan->n_end * sizeof(double4), st) != cudaSuccess)
+    if (d_k_im && plan->d != 3) return BHS_ERR_UNSUPPORTED;
+    if (cudaMallocAsync((void**)&rad, (size_t)nsys * B * plan->n_end * 4 * sizeof(cplx), st) != cudaSuccess)
         return BHS_ERR_ALLOC;
     AsmWork w;
     w.rad = rad; w.rowf = nullptr; w.colf = nullptr; w.diag = (cplx*)d_out;
-    int rc = run_factors(plan, B, nsys, d_radii, d_k, d_eta, d_alpha, d_beta, w, true, st);
+    int rc = run_factors(plan, B, nsys, d_radii, d_k, d_k_im, d_eta, d_alpha, d_beta, w, true, st);
     cudaFreeAsync(rad, st);
     return rc;
 }
@@ -498,6 +576,7 @@ __global__ void __launch_bounds__(128) rhs_expand_kernel(int d, int B, int H, in
                                                          const double* __restrict__ centers,
                                                          const double* __restrict__ radii,
                                                          const double* __restrict__ k_in,
+                                                         const double* __restrict__ k_in_im,
                                                          const double* __restrict__ dir, const cplx* __restrict__ alpha,
                                                          const cplx* __restrict__ beta, const double* __restrict__ qdirs,
                                                          const cplx* __restrict__ WY, cplx* __restrict__ out) {
@@ -514,13 +593,16 @@ __global__ void __launch_bounds__(128) rhs_expand_kernel(int d, int B, int H, in
                 dy += dir[a] * qdirs[(int64_t)a * Q + q];
                 dc += dir[a] * centers[(int64_t)b * d + a];
             }
-            double ph = k * (rho * dy + dc), sn, co;
+            const double kim = k_in_im ? k_in_im[s] : 0.0;
+            const double sarg = rho * dy + dc;
+            double ph = k * sarg, sn, co;
             sincos(ph, &sn, &co);
             cplx u = cmake(co, sn);
+            if (kim != 0.0) u = cscale(u, exp(-kim * sarg));  // exp(i (k + i kim) d.x)
             cplx al = alpha ? alpha[b] : cmake(1.0, 0.0);
             cplx be = beta ? beta[b] : cmake(0.0, 0.0);
             // -alpha u - beta (i k d.y) u
-            cplx t = cadd(al, cmul(be, cmake(0.0, k * dy)));
+            cplx t = cadd(al, cmul(be, cmake(-kim * dy, k * dy)));
             v = cmul(cmake(-t.x, -t.y), u);
         }
         s_g[q] = v;
@@ -538,8 +620,8 @@ __global__ void __launch_bounds__(128) rhs_expand_kernel(int d, int B, int H, in
 }
 
 extern "C" int bhs_rhs_expand(const bhs_plan_t* plan, int B, int nsys, const double* d_g, const double* d_centers,
-                              const double* d_radii, const double* d_k_in, const double* d_dir, const double* d_alpha,
-                              const double* d_beta, double* d_out, void* stream) {
+                              const double* d_radii, const double* d_k_in, const double* d_k_in_im, const double* d_dir,
+                              const double* d_alpha, const double* d_beta, double* d_out, void* stream) {
     if (!plan || B <= 0 || nsys <= 0 || !d_out) return BHS_ERR_INVALID;
     if (!d_g && (!d_centers || !d_radii || !d_k_in || !d_dir)) return BHS_ERR_INVALID;
     if (nsys > 65535 || B > 65535) return BHS_ERR_UNSUPPORTED;
@@ -549,7 +631,7 @@ extern "C" int bhs_rhs_expand(const bhs_plan_t* plan, int B, int nsys, const dou
     dim3 grid((plan->H + 127) / 128, B, nsys);
     bhs_prof_begin(BHS_PROF_RHS_EXPAND, (cudaStream_t)stream);
     rhs_expand_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(plan->d, B, plan->H, plan->Q, (const cplx*)d_g,
-                                                                 d_centers, d_radii, d_k_in, d_dir,
+                                                                 d_centers, d_radii, d_k_in, d_k_in_im, d_dir,
                                                                  (const cplx*)d_alpha, (const cplx*)d_beta,
                                                                  plan->d_qdirs, plan->d_WY, (cplx*)d_out);
     bhs_prof_end(BHS_PROF_RHS_EXPAND, 0.0, (cudaStream_t)stream);

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <map>
 #include <new>
+#include <thread>
 
 #include "plan.h"
 
@@ -233,10 +234,12 @@ static int build_coupling(bhs_plan* p) {
     }
     // terms[(h_row, h'_col)] : row = h (harmonic of ball b), col = h' (harmonic of ball b')
     std::vector<std::vector<Term>> terms((size_t)H * H);
-    int64_t nterms = 0;
-    if (d == 3) {
-        // memoise the theta integral over (n', |m'|, n, |m|, n'') -- |m''| is fixed by the sign pattern
-        for (int h = 0; h < H; ++h) {
+    // rows h are independent: split them over host threads (the triple integrals are long-double quadratures,
+    // 2.5e9 multiply-adds at n_end = 39)
+    if (d != 3 && d != 4) return BHS_ERR_UNSUPPORTED;
+    const std::map<std::vector<int>, int>& lk2 = lookup2;  // read-only from here on
+    auto row_work = [&](int h, int64_t& cnt) {
+        if (d == 3) {
             int n = tab[h * 2], m = tab[h * 2 + 1];
             for (int hp = 0; hp < H; ++hp) {
                 int np = tab[hp * 2], mp = tab[hp * 2 + 1];
@@ -245,13 +248,11 @@ static int build_coupling(bhs_plan* p) {
                 for (int n2 = std::abs(n - np); n2 <= n + np; n2 += 2) {
                     if (n2 < std::abs(m2)) continue;
                     ld g = triple(0, np, std::abs(mp), n, std::abs(m), n2, std::abs(m2)) * inv_s2pi;
-                    tv.push_back({lookup2[{n2, m2}], (double)(cd * g)});
-                    ++nterms;
+                    tv.push_back({lk2.at({n2, m2}), (double)(cd * g)});
+                    ++cnt;
                 }
             }
-        }
-    } else if (d == 4) {
-        for (int h = 0; h < H; ++h) {
+        } else {
             int n = tab[h * 3], l = tab[h * 3 + 1], m = tab[h * 3 + 2];
             for (int hp = 0; hp < H; ++hp) {
                 int np = tab[hp * 3], lp = tab[hp * 3 + 1], mp = tab[hp * 3 + 2];
@@ -263,14 +264,25 @@ static int build_coupling(bhs_plan* p) {
                     for (int n2 = std::abs(n - np); n2 <= n + np; n2 += 2) {
                         if (n2 < l2) continue;
                         ld g = triple(0, np, lp, n, l, n2, l2) * g1 * inv_s2pi;
-                        tv.push_back({lookup2[{n2, l2, m2}], (double)(cd * g)});
-                        ++nterms;
+                        tv.push_back({lk2.at({n2, l2, m2}), (double)(cd * g)});
+                        ++cnt;
                     }
                 }
             }
         }
-    } else {
-        return BHS_ERR_UNSUPPORTED;
+    };
+    int64_t nterms = 0;
+    {
+        unsigned hw = std::thread::hardware_concurrency();
+        int T = (int)std::min<unsigned>(hw ? hw : 1, 16);
+        if ((int64_t)H * H < 4096) T = 1;
+        std::vector<int64_t> cnts(T, 0);
+        std::vector<std::thread> pool;
+        for (int t = 1; t < T; ++t)
+            pool.emplace_back([&, t]() { for (int h = t; h < H; h += T) row_work(h, cnts[t]); });
+        for (int h = 0; h < H; h += T) row_work(h, cnts[0]);
+        for (auto& th : pool) th.join();
+        for (int64_t c : cnts) nterms += c;
     }
     p->coupling_terms = nterms;
 

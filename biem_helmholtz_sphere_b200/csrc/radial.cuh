@@ -15,3 +15,18 @@ __device__ __forceinline__ cplx sd_coef(int d, double k, double eta, double rho,
     for (int i = 0; i < d - 2; ++i) pk *= k;
     return cmake(pr * pk * eta * jn, pr * pk * k * jd);
 }
+
+// Complex wavenumber k = kr + i ki (3-D only): radz[((s*B + b)*L + n)*4 + q] = (j_n, j_n', h_n, h_n')[q](k_s rho_b), complex.
+// d_kr / d_ki == nullptr: every system uses the scalars.
+int launch_ball_radial_z(int d, int L, int B, int nsys, const double* d_radii, const double* d_kr, const double* d_ki,
+                         double kr_s, double ki_s, cplx* d_out, cudaStream_t st);
+
+// SD_n(rho) for complex k: rho^{d-1} k^{d-2} (eta j_n + i k j_n')
+__device__ __forceinline__ cplx sd_coef_z(int d, cplx k, double eta, double rho, cplx jn, cplx jd) {
+    double pr = 1.0;
+    for (int i = 0; i < d - 1; ++i) pr *= rho;
+    cplx pk = cmake(1.0, 0.0);
+    for (int i = 0; i < d - 2; ++i) pk = cmul(pk, k);
+    const cplx ikjd = cmul(cmake(-k.y, k.x), jd);  // i k j'
+    return cmul(cscale(pk, pr), cadd(cscale(jn, eta), ikjd));
+}

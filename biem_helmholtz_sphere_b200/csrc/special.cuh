@@ -206,3 +206,91 @@ __device__ void hankel_upward(int d, double x, int n_max, ArrR hr, ArrI hi) {
     if (shift > 0 || even_dim)
         for (int n = 0; n <= n_max; ++n) { hr[n] = hr[n + shift] * sc; hi[n] = hi[n + shift] * sc; }
 }
+
+// =====================================================================================================
+// Complex argument (complex wavenumber, Im k != 0), spherical family only (odd d):
+//   j_n(z) : downward Miller recurrence normalised on the closed forms j_0 / j_1 when n_top >= |z|, upward otherwise;
+//   h_n(z) = h_n^{(1)}(z) : UPWARD from h_0 = -i e^{iz}/z, h_1 = -(z + i) e^{iz}/z^2.  h is never formed as j + i y:
+//            for Im z > 0 it is exponentially smaller than j and y, and the sum would cancel.
+// Even d (cylindrical family) is not implemented for complex arguments (needs K_nu-type algorithms for H^{(1)}).
+// =====================================================================================================
+__device__ __forceinline__ cplx cexp_i(cplx z) {  // e^{i z}
+    double s, c;
+    sincos(z.x, &s, &c);
+    const double e = exp(-z.y);
+    return cmake(e * c, e * s);
+}
+__device__ __forceinline__ double cabs1(cplx a) { return fabs(a.x) + fabs(a.y); }
+__device__ __forceinline__ double cabs2(cplx a) { return hypot(a.x, a.y); }
+
+// Arrays of length n_top + 1 (complex); either may be skipped.  z != 0.
+template <typename ArrJ, typename ArrH>
+__device__ void sph_sequence_z(cplx z, int n_top, ArrJ aj, ArrH ah, bool want_j, bool want_h) {
+    const cplx iz = crecip(z);
+    const cplx eiz = cexp_i(z);                            // e^{iz}
+    const cplx emiz = cexp_i(cmake(-z.x, -z.y));           // e^{-iz}
+    if (want_h) {
+        // h0 = -i e^{iz} / z ; h1 = -(z + i) e^{iz} / z^2
+        cplx h0 = cmul(cmake(eiz.y, -eiz.x), iz);
+        cplx h1 = cmul(cmul(cmake(-z.x, -z.y - 1.0), eiz), cmul(iz, iz));
+        ah[0] = h0;
+        if (n_top >= 1) ah[1] = h1;
+        cplx hm = h0, hc = h1;
+        for (int n = 1; n < n_top; ++n) {
+            cplx hn = csub(cmul(cscale(iz, 2.0 * n + 1.0), hc), hm);
+            hm = hc; hc = hn;
+            ah[n + 1] = hn;
+        }
+    }
+    if (want_j) {
+        // sin z = (e^{iz} - e^{-iz}) / 2i, cos z = (e^{iz} + e^{-iz}) / 2
+        const cplx df = csub(eiz, emiz), sm = cadd(eiz, emiz);
+        const cplx sn = cmake(0.5 * df.y, -0.5 * df.x), cs = cscale(sm, 0.5);
+        cplx f0 = cmul(sn, iz);
+        cplx f1 = cmul(csub(f0, cs), iz);
+        const double az = cabs2(z);
+        if (az < 0.5) {
+            // series for j1 (cancellation in the closed form): z/3 (1 - z^2/10 (1 - z^2/28 (1 - z^2/54 (1 - z^2/88 (1 - z^2/130)))))
+            const cplx z2 = cmul(z, z);
+            cplx t = cmake(1.0, 0.0);
+            const double den[5] = {130.0, 88.0, 54.0, 28.0, 10.0};
+            for (int q = 0; q < 5; ++q) t = csub(cmake(1.0, 0.0), cmul(cscale(z2, 1.0 / den[q]), t));
+            f1 = cmul(cscale(z, 1.0 / 3.0), t);
+        }
+        if ((double)n_top + 1.0 <= az) {
+            aj[0] = f0;
+            if (n_top >= 1) aj[1] = f1;
+            cplx jm = f0, jc = f1;
+            for (int n = 1; n < n_top; ++n) {
+                cplx jn = csub(cmul(cscale(iz, 2.0 * n + 1.0), jc), jm);
+                jm = jc; jc = jn;
+                aj[n + 1] = jn;
+            }
+        } else {
+            const int M = miller_start(n_top, az) + (int)(2.0 * fabs(z.y));
+            cplx jp1 = cmake(0.0, 0.0), jc = cmake(1e-280, 0.0);
+            for (int m = M; m >= 1; --m) {
+                cplx jm1 = csub(cmul(cscale(iz, 2.0 * m + 1.0), jc), jp1);
+                jp1 = jc; jc = jm1;  // jc = order m-1
+                if (m - 1 <= n_top) aj[m - 1] = jc;
+                if (cabs1(jc) > 1e200) {
+                    const double sc = 1e-200;
+                    jc = cscale(jc, sc); jp1 = cscale(jp1, sc);
+                    for (int q = m - 1; q <= n_top; ++q) aj[q] = cscale(aj[q], sc);
+                }
+            }
+            // normalise on the larger of the two closed-form start values
+            cplx nrm;
+            if (cabs1(f0) >= cabs1(f1) || n_top == 0) {
+                nrm = (cabs1(f0) >= cabs1(f1)) ? cdiv(f0, jc) : cdiv(f1, jp1);
+            } else {
+                nrm = cdiv(f1, aj[1]);
+            }
+            for (int q = 0; q <= n_top; ++q) aj[q] = cmul(aj[q], nrm);
+        }
+    }
+}
+// derivative: z_n' = (n/z) z_n - z_{n+1}
+__device__ __forceinline__ cplx radial_deriv_z(int n, cplx iz, cplx zn, cplx znp1) {
+    return csub(cmul(cscale(iz, (double)n), zn), znp1);
+}

@@ -20,7 +20,7 @@
 
 struct UscatArgs {
     int d, L, H, B, flags;
-    double k, eta;
+    double k, k_im, eta;  // wavenumber k + i k_im (k_im != 0: 3-D only)
     const double* x;  // [d][P]
     int64_t P;
     const double* centers;  // [B][d]
@@ -35,16 +35,23 @@ struct UscatArgs {
 
 // ---- coefficient preparation ------------------------------------------------------------------------
 // generic: coefg[b][h] = density[b][h] * SD_{deg h}(rho_b) * (far ? (-i)^deg : 1)
-__global__ void uscat_coef_generic_kernel(int d, int L, int H, int B, double k, double eta, int far,
+// radz != nullptr: complex wavenumber, table (j, j', h, h') complex from launch_ball_radial_z
+__global__ void uscat_coef_generic_kernel(int d, int L, int H, int B, double k, double k_im, double eta, int far,
                                           const double* __restrict__ radii, const double4* __restrict__ rad,
-                                          const int32_t* __restrict__ deg, const cplx* __restrict__ density,
-                                          cplx* __restrict__ coefg) {
+                                          const cplx* __restrict__ radz, const int32_t* __restrict__ deg,
+                                          const cplx* __restrict__ density, cplx* __restrict__ coefg) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)B * H) return;
     int b = (int)(i / H), h = (int)(i % H);
     int n = deg[h];
-    double4 r = rad[(int64_t)b * L + n];
-    cplx sd = sd_coef(d, k, eta, radii[b], r.x, r.y);
+    cplx sd;
+    if (radz) {
+        const cplx* rz = radz + ((int64_t)b * L + n) * 4;
+        sd = sd_coef_z(d, cmake(k, k_im), eta, radii[b], rz[0], rz[1]);
+    } else {
+        double4 r = rad[(int64_t)b * L + n];
+        sd = sd_coef(d, k, eta, radii[b], r.x, r.y);
+    }
     cplx c = cmul(density[i], sd);
     if (far) c = cmul_ipow(c, -n);
     coefg[i] = c;
@@ -52,9 +59,10 @@ __global__ void uscat_coef_generic_kernel(int d, int L, int H, int B, double k, 
 // 3-D records, m-major over the PADDED band LMAX (multiple of 8, >= L): per ball [c0, c1, c2, rho] then for
 // (m, n = m..LMAX-1): (c_{n,+m}, c_{n,-m}) * SD_n * norm_{n,m}, zero for n >= L.  Block 0 also writes the
 // recurrence coefficients beta_{n,m} = (n^2 - m^2) / (4 n^2 - 1) in the same (m, n) order.
-__global__ void uscat_coef3d_kernel(int L, int LMAX, int B, double k, double eta, int far,
+__global__ void uscat_coef3d_kernel(int L, int LMAX, int B, double k, double k_im, double eta, int far,
                                     const double* __restrict__ centers, const double* __restrict__ radii,
-                                    const double4* __restrict__ rad, const double* __restrict__ norm,
+                                    const double4* __restrict__ rad, const cplx* __restrict__ radz,
+                                    const double* __restrict__ norm,
                                     const cplx* __restrict__ density, double* __restrict__ rec,
                                     double* __restrict__ beta) {
     const int npair = LMAX * (LMAX + 1) / 2;
@@ -71,9 +79,15 @@ __global__ void uscat_coef3d_kernel(int L, int LMAX, int B, double k, double eta
         if (b == 0) beta[e] = (double)(n * n - m * m) / (double)(4 * n * n - 1);
         double4 out = make_double4(0.0, 0.0, 0.0, 0.0);
         if (n < L) {
-            double4 r = rad[(int64_t)b * L + n];
             const int eL = m * L - m * (m - 1) / 2 + (n - m);
-            cplx sd = cscale(sd_coef(3, k, eta, radii[b], r.x, r.y), norm[eL]);
+            cplx sd;
+            if (radz) {
+                const cplx* rz = radz + ((int64_t)b * L + n) * 4;
+                sd = cscale(sd_coef_z(3, cmake(k, k_im), eta, radii[b], rz[0], rz[1]), norm[eL]);
+            } else {
+                double4 r = rad[(int64_t)b * L + n];
+                sd = cscale(sd_coef(3, k, eta, radii[b], r.x, r.y), norm[eL]);
+            }
             if (far) sd = cmul_ipow(sd, -n);
             cplx cp = cmul(density[(int64_t)b * H + n * n + m], sd);
             cplx cm = (m == 0) ? cmake(0.0, 0.0) : cmul(density[(int64_t)b * H + n * n + 2 * n + 1 - m], sd);
@@ -111,7 +125,7 @@ __global__ void uscat_coef3d_kernel(int L, int LMAX, int B, double k, double eta
             }                                                                   \
         }
 
-template <int LMAX>
+template <int LMAX, bool ZK>
 __global__ void __launch_bounds__(US3D_THREADS) uscat3d_kernel(UscatArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int L = a.L, B = a.B;
@@ -182,6 +196,23 @@ __global__ void __launch_bounds__(US3D_THREADS) uscat3d_kernel(UscatArgs a) {
             if (far) {
 #pragma unroll
                 for (int n = 0; n < LMAX; ++n) { hr[n] = 1.0; hi[n] = 0.0; }
+            } else if (ZK) {
+                // complex wavenumber: h_0 = -i e^{iz}/z, h_1 = -(z + i) e^{iz}/z^2, complex upward recurrence
+                const cplx z = cmake(k * r, a.k_im * r), iz = crecip(z), e = cexp_i(z);
+                cplx h0 = cmul(cmake(e.y, -e.x), iz);
+                cplx h1 = cmul(cmul(cmake(-z.x, -z.y - 1.0), e), cmul(iz, iz));
+                hr[0] = h0.x; hi[0] = h0.y;
+                if (LMAX > 1) { hr[1] = h1.x; hi[1] = h1.y; }
+#pragma unroll
+                for (int n = 1; n < LMAX - 1; ++n) {
+                    if (n + 1 < L) {
+                        const cplx cf = cscale(iz, 2.0 * n + 1.0);
+                        hr[n + 1] = fma(cf.x, hr[n], fma(-cf.y, hi[n], -hr[n - 1]));
+                        hi[n + 1] = fma(cf.x, hi[n], fma(cf.y, hr[n], -hi[n - 1]));
+                    } else {
+                        hr[n + 1] = 0.0; hi[n + 1] = 0.0;
+                    }
+                }
             } else {
                 const double z = k * r, iz = 1.0 / z;
                 double s, co;
@@ -377,13 +408,23 @@ __global__ void __launch_bounds__(US3D_THREADS) uscat3d_kernel(UscatArgs a) {
             }
             if (far) {
                 // (ik)^{-1} exp(-i k x.c_b), x as given (_biem.py:931-944)
-                double ph = -k * (x0 * rb[0] + x1 * rb[1] + x2 * rb[2]);
+                const double dotc = x0 * rb[0] + x1 * rb[1] + x2 * rb[2];
+                double ph = -k * dotc;
                 double s, co;
                 sincos(ph, &s, &co);
-                // (br + i bi) * (co + i s) * (-i / k)
-                double tr = br * co - bi * s, ti = br * s + bi * co;
-                br = ti / k;
-                bi = -tr / k;
+                if (ZK) {
+                    // exp(-i (k + i k_im) x.c) / (i (k + i k_im))
+                    const double g = exp(a.k_im * dotc);
+                    const cplx t = cmul(cmake(br, bi), cmake(g * co, g * s));
+                    const cplx q = cdiv(t, cmake(-a.k_im, k));
+                    br = q.x;
+                    bi = q.y;
+                } else {
+                    // (br + i bi) * (co + i s) * (-i / k)
+                    double tr = br * co - bi * s, ti = br * s + bi * co;
+                    br = ti / k;
+                    bi = -tr / k;
+                }
             }
             if (per_ball) {
                 if (active) a.out[p * B + (c * US3D_CB + bb)] = cmake(br, bi);
@@ -447,6 +488,18 @@ __global__ void __launch_bounds__(128) uscat_generic_kernel(UscatArgs a, HarmTab
             if (lane == 0) {
                 if (far) {
                     for (int n = 0; n < L; ++n) { Hr[n] = 1.0; Hi[n] = 0.0; }
+                } else if (a.k_im != 0.0) {
+                    // complex wavenumber (d = 3): complex upward recurrence, written as (re, im) into Hr / Hi
+                    const cplx z = cmake(a.k * r, a.k_im * r), iz = crecip(z), e = cexp_i(z);
+                    cplx hm = cmul(cmake(e.y, -e.x), iz);
+                    cplx hc = cmul(cmul(cmake(-z.x, -z.y - 1.0), e), cmul(iz, iz));
+                    Hr[0] = hm.x; Hi[0] = hm.y;
+                    if (L > 1) { Hr[1] = hc.x; Hi[1] = hc.y; }
+                    for (int n = 1; n < L - 1; ++n) {
+                        const cplx hn = csub(cmul(cscale(iz, 2.0 * n + 1.0), hc), hm);
+                        hm = hc; hc = hn;
+                        Hr[n + 1] = hn.x; Hi[n + 1] = hn.y;
+                    }
                 } else {
                     hankel_upward(d, a.k * r, L - 1, SmArr{Hr}, SmArr{Hi});
                 }
@@ -463,13 +516,22 @@ __global__ void __launch_bounds__(128) uscat_generic_kernel(UscatArgs a, HarmTab
             }
             if (far) {
                 // (ik)^{-(d-1)/2} exp(-i k x.c_b): k^{-p} e^{-i pi p / 2}, p = (d-1)/2
-                double pw = 0.5 * (d - 1);
-                double ang = -a.k * dot - 1.57079632679489661923 * pw;
-                double sn, co;
-                sincos(ang, &sn, &co);
-                double mag = pow(a.k, -pw);
-                double tr = (pr * co - pi * sn) * mag, ti = (pr * sn + pi * co) * mag;
-                pr = tr; pi = ti;
+                if (a.k_im != 0.0) {
+                    // d = 3: exp(-i (k + i k_im) x.c) / (i (k + i k_im))
+                    double sn, co;
+                    sincos(-a.k * dot, &sn, &co);
+                    const double g = exp(a.k_im * dot);
+                    const cplx q = cdiv(cmul(cmake(pr, pi), cmake(g * co, g * sn)), cmake(-a.k_im, a.k));
+                    pr = q.x; pi = q.y;
+                } else {
+                    double pw = 0.5 * (d - 1);
+                    double ang = -a.k * dot - 1.57079632679489661923 * pw;
+                    double sn, co;
+                    sincos(ang, &sn, &co);
+                    double mag = pow(a.k, -pw);
+                    double tr = (pr * co - pi * sn) * mag, ti = (pr * sn + pi * co) * mag;
+                    pr = tr; pi = ti;
+                }
             }
             if (per_ball) {
                 for (int o = 16; o > 0; o >>= 1) {
@@ -507,7 +569,7 @@ static inline int64_t align256(int64_t v) { return (v + 255) & ~(int64_t)255; }
 extern "C" int64_t bhs_uscat_workspace(const bhs_plan_t* plan, int B) {
     if (!plan || B <= 0) return BHS_ERR_INVALID;
     int64_t L = plan->n_end, LM = (L + 7) / 8 * 8, npair = LM * (LM + 1) / 2;
-    int64_t rad = align256((int64_t)B * L * sizeof(double4));
+    int64_t rad = align256((int64_t)B * L * 4 * sizeof(cplx));  // real (j, j', y, y') or complex (j, j', h, h') table
     int64_t c3 = align256((int64_t)B * (4 + 4 * npair) * sizeof(double)) + align256(npair * sizeof(double));
     int64_t cg = align256((int64_t)B * plan->H * sizeof(cplx));
     int64_t kbuf = 256;
@@ -518,33 +580,41 @@ template <int LMAX>
 static int launch_uscat3d(const UscatArgs& a, cudaStream_t st) {
     const int npair = LMAX * (LMAX + 1) / 2;
     size_t smem = (size_t)(2 * US3D_CB * (4 + 4 * npair) + npair) * sizeof(double);
-    cudaFuncSetAttribute(uscat3d_kernel<LMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int64_t blocks = (a.P + US3D_THREADS - 1) / US3D_THREADS;
     bhs_prof_begin(BHS_PROF_USCAT, st);
-    uscat3d_kernel<LMAX><<<(unsigned)blocks, US3D_THREADS, smem, st>>>(a);
+    if (a.k_im != 0.0) {
+        cudaFuncSetAttribute(uscat3d_kernel<LMAX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        uscat3d_kernel<LMAX, true><<<(unsigned)blocks, US3D_THREADS, smem, st>>>(a);
+    } else {
+        cudaFuncSetAttribute(uscat3d_kernel<LMAX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        uscat3d_kernel<LMAX, false><<<(unsigned)blocks, US3D_THREADS, smem, st>>>(a);
+    }
     bhs_prof_end(BHS_PROF_USCAT, 8.0 * (double)a.P * a.B * a.H, st);
     BHS_CHECK_LAUNCH();
     return BHS_OK;
 }
 
 extern "C" int bhs_uscat(const bhs_plan_t* plan, int B, const double* d_centers, const double* d_radii, double k,
-                         double eta, const double* d_density, const double* d_x, int64_t P, int flags, double* d_out,
-                         void* d_work, void* stream) {
+                         double k_im, double eta, const double* d_density, const double* d_x, int64_t P, int flags,
+                         double* d_out, void* d_work, void* stream) {
     if (!plan || B <= 0 || P < 0) return BHS_ERR_INVALID;
     if (P == 0) return BHS_OK;  // empty point set: nothing to do (the buffers of empty arrays may be null)
     if (!d_centers || !d_radii || !d_density || !d_x || !d_out || !d_work) return BHS_ERR_INVALID;
     if (!(k > 0.0)) return BHS_ERR_UNSUPPORTED;
+    if (k_im != 0.0 && plan->d != 3) return BHS_ERR_UNSUPPORTED;  // complex wavenumbers: spherical family only
     cudaStream_t st = (cudaStream_t)stream;
     const int d = plan->d, L = plan->n_end, H = plan->H;
     const int64_t npair = (int64_t)L * (L + 1) / 2;
     unsigned char* w = (unsigned char*)d_work;
     double4* d_rad = (double4*)(w + 256);
-    unsigned char* d_coef = w + 256 + align256((int64_t)B * L * sizeof(double4));
-    int rc = launch_ball_radial(d, L, B, 1, d_radii, nullptr, k, d_rad, st);
+    unsigned char* d_coef = w + 256 + align256((int64_t)B * L * 4 * sizeof(cplx));
+    const cplx* d_radz = (k_im != 0.0) ? (const cplx*)d_rad : nullptr;
+    int rc = d_radz ? launch_ball_radial_z(d, L, B, 1, d_radii, nullptr, nullptr, k, k_im, (cplx*)d_rad, st)
+                    : launch_ball_radial(d, L, B, 1, d_radii, nullptr, k, d_rad, st);
     if (rc) return rc;
     const int far = (flags & BHS_FLAG_FAR_FIELD) ? 1 : 0;
     UscatArgs a;
-    a.d = d; a.L = L; a.H = H; a.B = B; a.flags = flags; a.k = k; a.eta = eta;
+    a.d = d; a.L = L; a.H = H; a.B = B; a.flags = flags; a.k = k; a.k_im = k_im; a.eta = eta;
     a.x = d_x; a.P = P; a.centers = d_centers; a.radii = d_radii;
     a.coefg = nullptr; a.rec = nullptr; a.beta = plan->d_us_beta; a.idx = plan->d_idx; a.deg = plan->d_deg;
     a.out = (cplx*)d_out;
@@ -552,8 +622,8 @@ extern "C" int bhs_uscat(const bhs_plan_t* plan, int B, const double* d_centers,
         const int LM = (L + 7) / 8 * 8;
         const int64_t npm = (int64_t)LM * (LM + 1) / 2;
         double* d_beta = (double*)(d_coef + align256((int64_t)B * (4 + 4 * npm) * sizeof(double)));
-        uscat_coef3d_kernel<<<B, 128, 0, st>>>(L, LM, B, k, eta, far, d_centers, d_radii, d_rad, plan->d_us_norm,
-                                               (const cplx*)d_density, (double*)d_coef, d_beta);
+        uscat_coef3d_kernel<<<B, 128, 0, st>>>(L, LM, B, k, k_im, eta, far, d_centers, d_radii, d_rad, d_radz,
+                                               plan->d_us_norm, (const cplx*)d_density, (double*)d_coef, d_beta);
         BHS_CHECK_LAUNCH();
         a.rec = (const double*)d_coef;
         a.beta = d_beta;
@@ -564,9 +634,9 @@ extern "C" int bhs_uscat(const bhs_plan_t* plan, int B, const double* d_centers,
         return launch_uscat3d<32>(a, st);
     }
     int64_t tot = (int64_t)B * H;
-    uscat_coef_generic_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(d, L, H, B, k, eta, far, d_radii, d_rad,
-                                                                            plan->d_deg, (const cplx*)d_density,
-                                                                            (cplx*)d_coef);
+    uscat_coef_generic_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(d, L, H, B, k, k_im, eta, far, d_radii,
+                                                                            d_rad, d_radz, plan->d_deg,
+                                                                            (const cplx*)d_density, (cplx*)d_coef);
     BHS_CHECK_LAUNCH();
     a.coefg = (const cplx*)d_coef;
     int warps = 4;

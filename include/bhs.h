@@ -14,6 +14,9 @@
  *     objects the caller owns;
  *   - return value: 0 = ok, <0 = invalid argument (BHS_ERR_*), >0 = cudaError_t of a failed launch;
  *   - coordinate types are the chain trees 'a' (d=2), 'ba' (d=3), 'bba' (d=4): passed as `d`;
+ *   - wavenumbers are real arrays `d_k`; an optional `d_k_im` (NULL = real wavenumbers) adds imaginary parts
+ *     (absorbing media, Im k != 0).  Complex wavenumbers are implemented for d = 3 (spherical family: h_n by upward
+ *     recurrence from closed forms, never as j + i y); for d = 2, 4 they return BHS_ERR_UNSUPPORTED;
  *   - matrices are ROW-major (C order), exactly the reference's [..., B, harm, B', harm'] layout.
  */
 #ifndef BHS_H
@@ -86,8 +89,8 @@ int bhs_harmonics(const bhs_plan_t *plan, int use_double_band, const double *d_x
  * d_centers [B, d], d_radii [B], d_dir [d] (unit), d_out complex128 [nsys, B, H]. */
 int bhs_rhs_expand(const bhs_plan_t *plan, int B, int nsys, const double *d_g,
                    const double *d_centers, const double *d_radii, const double *d_k_in,
-                   const double *d_dir, const double *d_alpha, const double *d_beta,
-                   double *d_out, void *stream);
+                   const double *d_k_in_im, const double *d_dir, const double *d_alpha,
+                   const double *d_beta, double *d_out, void *stream);
 
 /* K4: system assembly --------------------------------------------------------------------------
  * A[s][(b,h),(b',h')] = SD_{n'}(rho_b') * ( b==b' ? delta (alpha h_n + beta k h_n')(k rho_b)
@@ -97,14 +100,14 @@ int bhs_rhs_expand(const bhs_plan_t *plan, int B, int nsys, const double *d_g,
  * ld >= N (elements); sys_stride in complex elements.  d_work: bhs_assemble_workspace() bytes. */
 int64_t bhs_assemble_workspace(const bhs_plan_t *plan, int B, int nsys);
 int bhs_assemble(const bhs_plan_t *plan, int B, int nsys, const double *d_centers,
-                 const double *d_radii, const double *d_k, const double *d_eta,
+                 const double *d_radii, const double *d_k, const double *d_k_im, const double *d_eta,
                  const double *d_alpha, const double *d_beta, double *d_A, int64_t ld,
                  int64_t sys_stride, void *d_work, void *stream);
 
 /* single-sphere shortcut diag[s, b, h] = SD_n (alpha h_n + beta k h_n')  (_biem.py:648-691) */
 int bhs_diag_coef(const bhs_plan_t *plan, int B, int nsys, const double *d_radii, const double *d_k,
-                  const double *d_eta, const double *d_alpha, const double *d_beta, double *d_out,
-                  void *stream);
+                  const double *d_k_im, const double *d_eta, const double *d_alpha, const double *d_beta,
+                  double *d_out, void *stream);
 
 /* K5: dense complex128 solve, row-major, blocked LU with tournament partial pivoting, trailing
  * update on FP64 tensor cores (DMMA).  Replaces batch_tensorsolve.btensorsolve -> zgesv
@@ -132,7 +135,7 @@ int bhs_zgemm_sub(int64_t M, int64_t N, int64_t K, const double *d_A, int64_t ld
  * BHS_FLAG_INNER) unless BHS_FLAG_FAR_FIELD. d_work: bhs_uscat_workspace() bytes. */
 int64_t bhs_uscat_workspace(const bhs_plan_t *plan, int B);
 int bhs_uscat(const bhs_plan_t *plan, int B, const double *d_centers, const double *d_radii,
-              double k, double eta, const double *d_density, const double *d_x, int64_t P,
+              double k, double k_im, double eta, const double *d_density, const double *d_x, int64_t P,
               int flags, double *d_out, void *d_work, void *stream);
 
 /* measurement helpers (used by bench.py) ------------------------------------------------------- */

@@ -44,7 +44,7 @@ def test_argument_validation_without_gpu():
     assert lib.bhs_zgesv_workspace(0, 1) == -1
     assert lib.bhs_zgesv_workspace(4096, 1) > 0
     assert lib.bhs_zgemm_workspace(64, 64, 0) == -1
-    assert lib.bhs_uscat(None, 1, None, None, 1.0, 1.0, None, None, 0, 0, None, None, None) == -1
+    assert lib.bhs_uscat(None, 1, None, None, 1.0, 0.0, 1.0, None, None, 0, 0, None, None, None) == -1
     with pytest.raises(ValueError):
         _lib.check(-1)
     with pytest.raises(NotImplementedError):
