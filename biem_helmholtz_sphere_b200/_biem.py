@@ -12,9 +12,8 @@ Inputs may be NumPy arrays or torch tensors (any device); results come back in t
 
 Deliberate differences from the reference (documented in DESIGN.md):
 * float32 inputs are up-cast; outputs are always complex128 (north_star: complex128 only);
-* complex wavenumbers (Im k != 0) are implemented for 3-D ('ba') -- h_n by complex upward recurrence from closed forms,
-  j_n by Miller's algorithm -- and raise ``NotImplementedError`` for 2-D / 4-D (cylindrical family) and in
-  ``point_source``;
+* complex wavenumbers (Im k != 0) take their own kernels: h_n^{(1)} by complex upward recurrence from orders 0, 1 (never
+  as j + i y), j_n by Miller's algorithm -- oracle-pinned against scipy's complex-argument Bessel functions;
 * leading batch axes of ``k`` WORK together with ``uin`` (the reference raises there); the
   semantics are "identical to a loop of scalar-k calls";
 * extra keyword ``keep_matrix`` (default True = reference behaviour) lets sweeps drop the N x N matrices.
@@ -312,8 +311,8 @@ def point_source(*, k: Array, source: Array, n: int) -> tuple[Callable[[Array], 
     ns = _NS(k, source)
 
     def _hankel(z, d: int, derivative: bool):
-        if np.iscomplexobj(z) if not isinstance(z, torch.Tensor) else z.is_complex():
-            raise NotImplementedError("point_source with a complex wavenumber is not implemented in the B200 path")
+        if z.is_complex() if isinstance(z, torch.Tensor) else np.iscomplexobj(z):
+            return ns.out(_ops.bessel_z(d, 2, n, _t(z, C128), derivative)[..., n])
         zt = _t(z, F64)
         return ns.out(_ops.bessel(d, 2, n, zt, derivative)[..., n])
 
@@ -545,8 +544,6 @@ def biem(
     shared_geom = all(int(np.prod(t.shape[:-1])) == 1 for t in (rad, al, be)) and int(np.prod(cen.shape[:-2])) == 1
     k_user = kk
     kk, kk_im = _split_k(kk)
-    if kk_im is not None and d != 3:
-        raise NotImplementedError("complex wavenumbers (Im k != 0) are implemented for 3-D ('ba') only")
     ks = kk.expand(batch_shape).reshape(K).contiguous()
     kis = None if kk_im is None else kk_im.expand(batch_shape).reshape(K).contiguous()
     ets = et.expand(batch_shape).reshape(K).contiguous()

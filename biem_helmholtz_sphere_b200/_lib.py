@@ -29,6 +29,7 @@ SIGNATURES = {
     "bhs_plan_quadrature": (i32, [vp, vp, vp]),
     "bhs_plan_coupling_stats": (i32, [vp, C.POINTER(i64), C.POINTER(i64)]),
     "bhs_bessel": (i32, [i32, i32, i32, i32, vp, i64, vp, vp]),
+    "bhs_bessel_z": (i32, [i32, i32, i32, i32, vp, vp, i64, vp, vp]),
     "bhs_harmonics": (i32, [vp, i32, vp, i64, vp, vp]),
     "bhs_rhs_expand": (i32, [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "bhs_assemble_workspace": (i64, [vp, i32, i32]),

@@ -43,6 +43,16 @@ def bessel(d: int, kind: int, n_max: int, x, derivative: bool = False) -> torch.
     return out
 
 
+def bessel_z(d: int, kind: int, n_max: int, z, derivative: bool = False) -> torch.Tensor:
+    """z_n^{(d)}(z) for complex arguments z, n = 0..n_max (kind J or H1) -> complex128 [*z.shape, n_max+1]   (bhs_bessel_z)."""
+    zt = torch.as_tensor(z, device=_dev()).to(C128)
+    zr, zi = zt.real.contiguous(), zt.imag.contiguous()
+    out = torch.empty(zt.shape + (n_max + 1,), dtype=C128, device=zt.device)
+    check(load().bhs_bessel_z(d, kind, int(derivative), n_max, ptr(zr), ptr(zi), zt.numel(), ptr(out), stream_ptr()),
+          "bhs_bessel_z")
+    return out
+
+
 def harmonics(d: int, n_end: int, xyz, double_band: bool = False) -> torch.Tensor:
     """Y_h at the directions of xyz [d, ...] -> complex128 [..., H]   (bhs_harmonics)."""
     plan = get_plan(d, n_end)

@@ -199,13 +199,13 @@ __global__ void factors_kernel(int d, int L, int H, int B, int nsys, const doubl
     if (diag) diag[i] = cmul(sd, sing);
 }
 
-// ---- complex wavenumber variants (3-D): same outputs, complex arguments -----------------------------------------
+// ---- complex wavenumber variants: same outputs, complex arguments -----------------------------------------
 struct SmArrZ {
     cplx* p;
     int stride;
     __device__ __forceinline__ cplx& operator[](int n) const { return p[(size_t)n * stride]; }
 };
-__global__ void pair_radial_z_kernel(int L2, int n_store, int B, int nsys, const double* __restrict__ kr,
+__global__ void pair_radial_z_kernel(int d, int L2, int n_store, int B, int nsys, const double* __restrict__ kr,
                                      const double* __restrict__ ki, const double* __restrict__ dist,
                                      cplx* __restrict__ hp) {
     extern __shared__ __align__(16) cplx smz[];
@@ -220,7 +220,7 @@ __global__ void pair_radial_z_kernel(int L2, int n_store, int B, int nsys, const
             continue;
         }
         const double r = dist[pr];
-        sph_sequence_z(cmake(kr[s] * r, ki[s] * r), L2 - 1, ah, ah, false, true);
+        radial_sequence_z(d, cmake(kr[s] * r, ki[s] * r), L2 - 1, ah, ah, false, true);
         for (int n = 0; n < L2; ++n) hp[i * L2 + n] = cmul_ipow(ah[n], n);
     }
     (void)n_store;
@@ -467,7 +467,6 @@ extern "C" int bhs_assemble(const bhs_plan_t* plan, int B, int nsys, const doubl
     cudaStream_t st = (cudaStream_t)stream;
     AsmWork w = carve(plan, B, nsys, d_work);
     bhs_prof_begin(BHS_PROF_ASM_PRE, st);
-    if (d_k_im && plan->d != 3) return BHS_ERR_UNSUPPORTED;  // complex wavenumbers: spherical family only
     int rc = run_factors(plan, B, nsys, d_radii, d_k, d_k_im, d_eta, d_alpha, d_beta, w, false, st);
     if (rc) return rc;
     const int64_t np = (int64_t)B * B;
@@ -486,14 +485,14 @@ extern "C" int bhs_assemble(const bhs_plan_t* plan, int B, int nsys, const doubl
         if (blocks > 148 * 8) blocks = 148 * 8;
         if (d_k_im) {
             int Tz = 64;
-            const int ns = plan->L2 + 1;
+            const int ns = plan->L2 + 1 + shift;
             while (Tz > 32 && (size_t)ns * Tz * sizeof(cplx) > 160 * 1024) Tz >>= 1;
             size_t smz = (size_t)ns * Tz * sizeof(cplx);
             if (smz > 200 * 1024) return BHS_ERR_UNSUPPORTED;
             cudaFuncSetAttribute(pair_radial_z_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smz);
             int64_t bz = (total + Tz - 1) / Tz;
             if (bz > 148 * 8) bz = 148 * 8;
-            pair_radial_z_kernel<<<(unsigned)bz, Tz, smz, st>>>(plan->L2, ns, B, nsys, d_k, d_k_im, w.dist, w.hp);
+            pair_radial_z_kernel<<<(unsigned)bz, Tz, smz, st>>>(d, plan->L2, ns, B, nsys, d_k, d_k_im, w.dist, w.hp);
         } else if (smem > 200 * 1024) {
             if (blocks > 32) blocks = 32;
             double* scratch = nullptr;
@@ -561,7 +560,6 @@ extern "C" int bhs_diag_coef(const bhs_plan_t* plan, int B, int nsys, const doub
     // needs only the radial table: carve it out of a temporary allocation
     cudaStream_t st = (cudaStream_t)stream;
     double4* rad = nullptr;
-    if (d_k_im && plan->d != 3) return BHS_ERR_UNSUPPORTED;
     if (cudaMallocAsync((void**)&rad, (size_t)nsys * B * plan->n_end * 4 * sizeof(cplx), st) != cudaSuccess)
         return BHS_ERR_ALLOC;
     AsmWork w;

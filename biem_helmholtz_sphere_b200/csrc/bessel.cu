@@ -129,3 +129,47 @@ extern "C" int bhs_fp64_peak(int shape, int iters, double* tflops_out) {
     *tflops_out = best;
     return BHS_OK;
 }
+
+// ---- K1, complex argument ------------------------------------------------------------------------------------
+// out[i, n] = z_n^{(d)}(x_i) (kind J or H1) or its derivative, x_i = xr[i] + i xi[i] != 0.  One thread per argument, order
+// sequences in shared memory (order-major); used for the complex-wavenumber point source and by the parity tests.
+struct StridedArrZ2 {
+    cplx* base;
+    int stride;
+    __device__ __forceinline__ cplx& operator[](int n) const { return base[(size_t)n * stride]; }
+};
+
+__global__ void bessel_z_kernel(int d, int kind, int derivative, int n_max, int n_store, const double* __restrict__ xr,
+                                const double* __restrict__ xi, int64_t nx, cplx* __restrict__ out) {
+    extern __shared__ __align__(16) cplx smz[];
+    const int T = blockDim.x;
+    StridedArrZ2 arr{smz + threadIdx.x, T};
+    for (int64_t i = (int64_t)blockIdx.x * T + threadIdx.x; i < nx; i += (int64_t)gridDim.x * T) {
+        const cplx z = cmake(xr[i], xi[i]);
+        const bool want_j = kind == BHS_KIND_J;
+        radial_sequence_z(d, z, n_max + 1, arr, arr, want_j, !want_j);
+        const cplx iz = crecip(z);
+        for (int n = 0; n <= n_max; ++n)
+            out[i * (n_max + 1) + n] = derivative ? radial_deriv_z(n, iz, arr[n], arr[n + 1]) : arr[n];
+    }
+}
+
+extern "C" int bhs_bessel_z(int d, int kind, int derivative, int n_max, const double* d_x_re, const double* d_x_im,
+                            int64_t nx, double* d_out, void* stream) {
+    if (d < 2 || (kind != BHS_KIND_J && kind != BHS_KIND_H1) || n_max < 0 || nx < 0) return BHS_ERR_INVALID;
+    if (nx == 0) return BHS_OK;
+    if (!d_x_re || !d_x_im || !d_out) return BHS_ERR_INVALID;
+    const int shift = (d & 1) ? (d - 3) / 2 : d / 2 - 1;
+    const int n_store = n_max + 2 + shift + 1;
+    int T = 64;
+    while (T > 32 && (size_t)n_store * T * sizeof(cplx) > 160 * 1024) T >>= 1;
+    const size_t smem = (size_t)n_store * T * sizeof(cplx);
+    if (smem > 200 * 1024) return BHS_ERR_UNSUPPORTED;
+    cudaFuncSetAttribute(bessel_z_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int64_t blocks = (nx + T - 1) / T;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    bessel_z_kernel<<<(unsigned)blocks, T, smem, (cudaStream_t)stream>>>(d, kind, derivative, n_max, n_store, d_x_re, d_x_im,
+                                                                         nx, (cplx*)d_out);
+    BHS_CHECK_LAUNCH();
+    return BHS_OK;
+}

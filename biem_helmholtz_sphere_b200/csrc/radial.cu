@@ -61,7 +61,7 @@ int launch_ball_radial(int d, int L, int B, int nsys, const double* d_radii, con
     return BHS_OK;
 }
 
-// ---- complex wavenumber (3-D / odd d only) -------------------------------------------------------------------
+// ---- complex wavenumber -------------------------------------------------------------------
 // radz[((s*B + b)*L + n)*4 + {0,1,2,3}] = ( j_n, j_n', h_n, h_n' )(k_s rho_b), all complex, k_s = kr[s] + i ki[s]
 struct StridedArrZ {
     cplx* base;
@@ -69,7 +69,7 @@ struct StridedArrZ {
     __device__ __forceinline__ cplx& operator[](int n) const { return base[(size_t)n * stride]; }
 };
 
-__global__ void ball_radial_z_kernel(int L, int n_store, int B, int nsys, const double* __restrict__ radii,
+__global__ void ball_radial_z_kernel(int d, int L, int n_store, int B, int nsys, const double* __restrict__ radii,
                                      const double* __restrict__ kr, const double* __restrict__ ki, double kr_s, double ki_s,
                                      cplx* __restrict__ out) {
     extern __shared__ __align__(16) cplx smz[];
@@ -81,7 +81,7 @@ __global__ void ball_radial_z_kernel(int L, int n_store, int B, int nsys, const 
         int s = (int)(i / B), b = (int)(i % B);
         const double rho = radii[b];
         const cplx z = cmake((kr ? kr[s] : kr_s) * rho, (ki ? ki[s] : ki_s) * rho);
-        sph_sequence_z(z, L, aj, ah, true, true);
+        radial_sequence_z(d, z, L, aj, ah, true, true);
         const cplx iz = crecip(z);
         for (int n = 0; n < L; ++n) {
             const cplx jn = aj[n], hn = ah[n];
@@ -96,9 +96,8 @@ __global__ void ball_radial_z_kernel(int L, int n_store, int B, int nsys, const 
 
 int launch_ball_radial_z(int d, int L, int B, int nsys, const double* d_radii, const double* d_kr, const double* d_ki,
                          double kr_s, double ki_s, cplx* d_out, cudaStream_t st) {
-    if ((d & 1) == 0) return BHS_ERR_UNSUPPORTED;  // cylindrical family: real wavenumbers only
-    if (d != 3) return BHS_ERR_UNSUPPORTED;
-    int n_store = L + 2;
+    const int shift = (d & 1) ? (d - 3) / 2 : d / 2 - 1;
+    int n_store = L + 2 + shift;
     int T = 64;
     while (T > 32 && (size_t)2 * n_store * T * sizeof(cplx) > 160 * 1024) T >>= 1;
     size_t smem = (size_t)2 * n_store * T * sizeof(cplx);
@@ -107,7 +106,7 @@ int launch_ball_radial_z(int d, int L, int B, int nsys, const double* d_radii, c
     int64_t total = (int64_t)B * nsys;
     int64_t blocks = (total + T - 1) / T;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    ball_radial_z_kernel<<<(unsigned)blocks, T, smem, st>>>(L, n_store, B, nsys, d_radii, d_kr, d_ki, kr_s, ki_s, d_out);
+    ball_radial_z_kernel<<<(unsigned)blocks, T, smem, st>>>(d, L, n_store, B, nsys, d_radii, d_kr, d_ki, kr_s, ki_s, d_out);
     BHS_CHECK_LAUNCH();
     return BHS_OK;
 }

@@ -257,7 +257,9 @@ __device__ void sph_sequence_z(cplx z, int n_top, ArrJ aj, ArrH ah, bool want_j,
             for (int q = 0; q < 5; ++q) t = csub(cmake(1.0, 0.0), cmul(cscale(z2, 1.0 / den[q]), t));
             f1 = cmul(cscale(z, 1.0 / 3.0), t);
         }
-        if ((double)n_top + 1.0 <= az) {
+        // Upward recurrence only in the oscillatory region close to the real axis: away from it j_n behaves like the
+        // modified function i_n, which is the MINIMAL solution for every n (z = 40i lost 9 digits at n = 30 going upward).
+        if ((double)n_top + 1.0 <= fabs(z.x) && fabs(z.y) <= 1.0) {
             aj[0] = f0;
             if (n_top >= 1) aj[1] = f1;
             cplx jm = f0, jc = f1;
@@ -293,4 +295,175 @@ __device__ void sph_sequence_z(cplx z, int n_top, ArrJ aj, ArrH ah, bool want_j,
 // derivative: z_n' = (n/z) z_n - z_{n+1}
 __device__ __forceinline__ cplx radial_deriv_z(int n, cplx iz, cplx zn, cplx znp1) {
     return csub(cmul(cscale(iz, (double)n), zn), znp1);
+}
+
+// ---- cylindrical family, complex argument -----------------------------------------------------------------
+__device__ __forceinline__ cplx csqrt_(cplx a) {
+    const double m = hypot(a.x, a.y);
+    if (m == 0.0) return cmake(0.0, 0.0);
+    double sr = sqrt(0.5 * (m + fabs(a.x)));
+    double si = 0.5 * a.y / sr;
+    if (a.x >= 0.0) return cmake(sr, si);
+    return cmake(fabs(si), a.y >= 0.0 ? sr : -sr);
+}
+__device__ __forceinline__ cplx clog_(cplx a) { return cmake(log(hypot(a.x, a.y)), atan2(a.y, a.x)); }
+__device__ __forceinline__ cplx cexp_(cplx a) {
+    double s, c;
+    sincos(a.y, &s, &c);
+    const double e = exp(a.x);
+    return cmake(e * c, e * s);
+}
+
+// H^{(1)}_0(z), H^{(1)}_1(z) by the Hankel asymptotic series, |z| >= 18 (smallest term ~ e^{-2|z|} < 3e-16)
+__device__ inline void cyl_h01_asym(cplx z, cplx& h0, cplx& h1) {
+    const cplx iz = crecip(z);
+    const cplx pref = csqrt_(cscale(iz, BHS_2_PI));  // sqrt(2 / (pi z))
+    const cplx e = cexp_i(z);
+    const double r2 = 0.70710678118654752440;
+#pragma unroll
+    for (int nu = 0; nu < 2; ++nu) {
+        const double mu = 4.0 * nu * nu;
+        cplx sum = cmake(1.0, 0.0), term = cmake(1.0, 0.0);
+        const cplx i8z = cmul(cmake(0.0, 0.125), iz);  // i / (8 z)
+        double last = 1.0;
+        for (int kk = 1; kk < 80; ++kk) {
+            const double f = (mu - (2.0 * kk - 1.0) * (2.0 * kk - 1.0)) / kk;
+            const cplx nt = cmul(term, cscale(i8z, f));
+            const double mag = cabs1(nt);
+            if (mag >= last && kk > 2) break;
+            term = nt;
+            last = mag;
+            sum = cadd(sum, term);
+            if (mag < 1e-18) break;
+        }
+        // e^{i(z - nu pi/2 - pi/4)} = e^{iz} * e^{-i pi/4} * (-i)^nu
+        cplx ph = cmul(e, cmake(r2, -r2));
+        if (nu == 1) ph = cmake(ph.y, -ph.x);
+        const cplx v = cmul(cmul(pref, ph), sum);
+        if (nu == 0) h0 = v; else h1 = v;
+    }
+}
+
+// K_0(w), K_1(w) for Re w > 0, |w| >= 2: Steed's continued fraction CF2 (Temme; Numerical Recipes `bessik`, mu = 0),
+// in complex arithmetic.  Used through H^{(1)}_nu(z) = (2 / (pi i)) e^{-i nu pi / 2} K_nu(-i z).
+__device__ inline void cyl_k01_cf2(cplx w, cplx& k0, cplx& k1) {
+    cplx b = cscale(cadd(cmake(1.0, 0.0), w), 2.0);
+    cplx d = crecip(b), h = d, delh = d;
+    cplx q1 = cmake(0.0, 0.0), q2 = cmake(1.0, 0.0);
+    const double a1 = 0.25;  // 1/4 - mu^2
+    cplx q = cmake(a1, 0.0), c = q;
+    double a = -a1;
+    cplx s = cadd(cmake(1.0, 0.0), cmul(q, delh));
+    for (int i = 2; i < 2000; ++i) {
+        a -= 2.0 * (i - 1);
+        c = cscale(c, -a / i);
+        const cplx qnew = cscale(csub(q1, cmul(b, q2)), 1.0 / a);
+        q1 = q2;
+        q2 = qnew;
+        q = cadd(q, cmul(c, qnew));
+        b = cadd(b, cmake(2.0, 0.0));
+        d = crecip(cadd(b, cscale(d, a)));
+        delh = cmul(csub(cmul(b, d), cmake(1.0, 0.0)), delh);
+        h = cadd(h, delh);
+        const cplx dels = cmul(q, delh);
+        s = cadd(s, dels);
+        if (cabs1(dels) < 1e-17 * cabs1(s)) break;
+    }
+    h = cscale(h, a1);
+    // K_0 = sqrt(pi / (2 w)) e^{-w} / s ;  K_1 = K_0 (w + 1/2 - h) / w
+    const cplx iw = crecip(w);
+    k0 = cmul(cmul(csqrt_(cscale(iw, 1.57079632679489661923)), cexp_(cmake(-w.x, -w.y))), crecip(s));
+    k1 = cmul(cmul(k0, csub(cadd(w, cmake(0.5, 0.0)), h)), iw);
+}
+
+// J_0..J_{n_top} (Miller, normalised on e^{-+iz} = J_0 + 2 sum (-+i)^k J_k, which has no cancellation on the side of the
+// real axis where it is used) and H^{(1)}_0..H^{(1)}_{n_top} (upward from the orders 0, 1).  z != 0.
+template <typename ArrJ, typename ArrH>
+__device__ void cyl_sequence_z(cplx z, int n_top, ArrJ aj, ArrH ah, bool want_j, bool want_h) {
+    const double az = cabs2(z);
+    const cplx iz = crecip(z);
+    const bool asym = az >= 18.0;
+    const bool via_k = !asym && z.y > 3.0 && az >= 2.0;  // H from K_nu(-iz); else (near the real axis) from J + i Y
+    const bool need_miller = want_j || (want_h && !asym && !via_k);
+    cplx j0 = cmake(0.0, 0.0), j1 = j0, ysum = j0, y1sum = j0;
+    if (need_miller) {
+        int M = miller_start(want_j ? n_top : 1, az) + (int)(2.0 * fabs(z.y));
+        M += (M & 1);  // even
+        const bool up = z.y >= 0.0;  // normalise on e^{-iz} (|.| = e^{Im z}) above the real axis, e^{+iz} below
+        cplx jp1 = cmake(0.0, 0.0), jc = cmake(1e-280, 0.0);
+        cplx nsum = cmake(0.0, 0.0);
+        for (int m = M; m >= 1; --m) {
+            // at loop top: jc = J_m, jp1 = J_{m+1}
+            const cplx jm1 = csub(cmul(cscale(iz, 2.0 * m), jc), jp1);
+            // 2 (-+i)^m J_m
+            nsum = cadd(nsum, cscale(cmul_ipow(jc, up ? -m : m), 2.0));
+            if ((m & 1) == 0) {
+                const int kk = m >> 1;
+                const double sg = (kk & 1) ? -1.0 : 1.0;
+                ysum = cadd(ysum, cscale(jc, sg / kk));
+                y1sum = cadd(y1sum, cscale(csub(jm1, jp1), sg / kk));
+            }
+            jp1 = jc;
+            jc = jm1;  // order m-1
+            if (want_j && m - 1 <= n_top) aj[m - 1] = jc;
+            if (cabs1(jc) > 1e200) {
+                const double sc = 1e-200;
+                jc = cscale(jc, sc); jp1 = cscale(jp1, sc); nsum = cscale(nsum, sc);
+                ysum = cscale(ysum, sc); y1sum = cscale(y1sum, sc);
+                if (want_j) for (int q = m - 1; q <= n_top; ++q) aj[q] = cscale(aj[q], sc);
+            }
+        }
+        nsum = cadd(nsum, jc);  // + J_0
+        const cplx target = cexp_i(up ? cmake(-z.x, -z.y) : z);
+        const cplx nrm = cdiv(target, nsum);
+        j0 = cmul(jc, nrm);
+        j1 = cmul(jp1, nrm);
+        ysum = cmul(ysum, nrm);
+        y1sum = cmul(y1sum, nrm);
+        if (want_j) for (int q = 0; q <= n_top; ++q) aj[q] = cmul(aj[q], nrm);
+    }
+    if (want_h) {
+        cplx h0, h1;
+        if (asym) {
+            cyl_h01_asym(z, h0, h1);
+        } else if (via_k) {
+            cplx k0, k1;
+            cyl_k01_cf2(cmake(z.y, -z.x), k0, k1);  // w = -i z
+            // H0 = (2 / (pi i)) K0 = -i (2/pi) K0 ;  H1 = -(2/pi) K1
+            h0 = cscale(cmake(k0.y, -k0.x), BHS_2_PI);
+            h1 = cscale(k1, -BHS_2_PI);
+        } else {
+            const cplx lg = cadd(clog_(cscale(z, 0.5)), cmake(BHS_EULER, 0.0));
+            const cplx y0 = cscale(csub(cmul(lg, j0), cscale(ysum, 2.0)), BHS_2_PI);
+            const cplx y1 = cscale(cadd(csub(cmul(lg, j1), cmul(j0, iz)), y1sum), BHS_2_PI);
+            h0 = cadd(j0, cmake(-y0.y, y0.x));
+            h1 = cadd(j1, cmake(-y1.y, y1.x));
+        }
+        ah[0] = h0;
+        if (n_top >= 1) ah[1] = h1;
+        cplx hm = h0, hc = h1;
+        for (int n = 1; n < n_top; ++n) {
+            const cplx hn = csub(cmul(cscale(iz, 2.0 * n), hc), hm);
+            hm = hc; hc = hn;
+            ah[n + 1] = hn;
+        }
+    }
+}
+
+// z_n^{(d)} for n = 0..n_max_plus (complex argument), any d >= 2: arrays must hold n_max_plus + 1 + shift entries.
+template <typename ArrJ, typename ArrH>
+__device__ void radial_sequence_z(int d, cplx z, int n_max_plus, ArrJ aj, ArrH ah, bool want_j, bool want_h) {
+    const int even_dim = (d & 1) == 0;
+    const int shift = even_dim ? d / 2 - 1 : (d - 3) / 2;
+    if (even_dim) cyl_sequence_z(z, n_max_plus + shift, aj, ah, want_j, want_h);
+    else sph_sequence_z(z, n_max_plus + shift, aj, ah, want_j, want_h);
+    if (shift > 0 || even_dim) {
+        cplx sc = cmake(even_dim ? BHS_SQRT_PI_2 : 1.0, 0.0);
+        const cplx iz = crecip(z);
+        for (int s = 0; s < shift; ++s) sc = cmul(sc, iz);
+        for (int n = 0; n <= n_max_plus; ++n) {
+            if (want_j) aj[n] = cmul(aj[n + shift], sc);
+            if (want_h) ah[n] = cmul(ah[n + shift], sc);
+        }
+    }
 }

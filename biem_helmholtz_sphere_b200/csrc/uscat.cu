@@ -453,6 +453,10 @@ struct SmArr {
     double* p;
     __device__ __forceinline__ double& operator[](int n) const { return p[n]; }
 };
+struct SmArrC {
+    cplx* p;
+    __device__ __forceinline__ cplx& operator[](int n) const { return p[n]; }
+};
 
 __global__ void __launch_bounds__(128) uscat_generic_kernel(UscatArgs a, HarmTables tb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -467,6 +471,8 @@ __global__ void __launch_bounds__(128) uscat_generic_kernel(UscatArgs a, HarmTab
     harm_smem_carve(base, L, F, E);
     double* Hr = reinterpret_cast<double*>(base + harm_bytes);
     double* Hi = Hr + (L + 2 + shift);
+    cplx* Hz = reinterpret_cast<cplx*>(Hr);  // complex-wavenumber view of the same scratch
+    const bool zk = a.k_im != 0.0;
     const bool far = a.flags & BHS_FLAG_FAR_FIELD, inner = a.flags & BHS_FLAG_INNER, per_ball = a.flags & BHS_FLAG_PER_BALL;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     for (int64_t p = (int64_t)blockIdx.x * warps + warp; p < a.P; p += (int64_t)gridDim.x * warps) {
@@ -487,19 +493,14 @@ __global__ void __launch_bounds__(128) uscat_generic_kernel(UscatArgs a, HarmTab
             warp_harmonic_tables(tb, L, dx, F, E, lane);
             if (lane == 0) {
                 if (far) {
-                    for (int n = 0; n < L; ++n) { Hr[n] = 1.0; Hi[n] = 0.0; }
-                } else if (a.k_im != 0.0) {
-                    // complex wavenumber (d = 3): complex upward recurrence, written as (re, im) into Hr / Hi
-                    const cplx z = cmake(a.k * r, a.k_im * r), iz = crecip(z), e = cexp_i(z);
-                    cplx hm = cmul(cmake(e.y, -e.x), iz);
-                    cplx hc = cmul(cmul(cmake(-z.x, -z.y - 1.0), e), cmul(iz, iz));
-                    Hr[0] = hm.x; Hi[0] = hm.y;
-                    if (L > 1) { Hr[1] = hc.x; Hi[1] = hc.y; }
-                    for (int n = 1; n < L - 1; ++n) {
-                        const cplx hn = csub(cmul(cscale(iz, 2.0 * n + 1.0), hc), hm);
-                        hm = hc; hc = hn;
-                        Hr[n + 1] = hn.x; Hi[n + 1] = hn.y;
+                    for (int n = 0; n < L; ++n) {
+                        if (zk) Hz[n] = cmake(1.0, 0.0);
+                        else { Hr[n] = 1.0; Hi[n] = 0.0; }
                     }
+                } else if (zk) {
+                    // complex wavenumber: the (Hr, Hi) scratch (2 (L + 2 + shift) doubles) holds the sequence as
+                    // L + shift interleaved complex values Hz[n]
+                    radial_sequence_z(d, cmake(a.k * r, a.k_im * r), L - 1, SmArrC{Hz}, SmArrC{Hz}, false, true);
                 } else {
                     hankel_upward(d, a.k * r, L - 1, SmArr{Hr}, SmArr{Hi});
                 }
@@ -509,7 +510,7 @@ __global__ void __launch_bounds__(128) uscat_generic_kernel(UscatArgs a, HarmTab
             for (int h = lane; h < a.H; h += 32) {
                 cplx y = harmonic_from_tables(tb, L, a.idx + (int64_t)h * s, F, E);
                 int n = a.deg[h];
-                cplx t = cmul(cmake(Hr[n], Hi[n]), y);
+                cplx t = cmul(zk ? Hz[n] : cmake(Hr[n], Hi[n]), y);
                 cplx c = a.coefg[(int64_t)b * a.H + h];
                 pr += t.x * c.x - t.y * c.y;
                 pi += t.x * c.y + t.y * c.x;
@@ -517,11 +518,13 @@ __global__ void __launch_bounds__(128) uscat_generic_kernel(UscatArgs a, HarmTab
             if (far) {
                 // (ik)^{-(d-1)/2} exp(-i k x.c_b): k^{-p} e^{-i pi p / 2}, p = (d-1)/2
                 if (a.k_im != 0.0) {
-                    // d = 3: exp(-i (k + i k_im) x.c) / (i (k + i k_im))
+                    // exp(-i (k + i k_im) x.c) * (i (k + i k_im))^{-(d-1)/2}   (principal branch, as numpy's power)
                     double sn, co;
                     sincos(-a.k * dot, &sn, &co);
                     const double g = exp(a.k_im * dot);
-                    const cplx q = cdiv(cmul(cmake(pr, pi), cmake(g * co, g * sn)), cmake(-a.k_im, a.k));
+                    const cplx lg = clog_(cmake(-a.k_im, a.k));
+                    const cplx pwz = cexp_(cscale(lg, -0.5 * (d - 1)));
+                    const cplx q = cmul(cmul(cmake(pr, pi), cmake(g * co, g * sn)), pwz);
                     pr = q.x; pi = q.y;
                 } else {
                     double pw = 0.5 * (d - 1);
@@ -601,7 +604,6 @@ extern "C" int bhs_uscat(const bhs_plan_t* plan, int B, const double* d_centers,
     if (P == 0) return BHS_OK;  // empty point set: nothing to do (the buffers of empty arrays may be null)
     if (!d_centers || !d_radii || !d_density || !d_x || !d_out || !d_work) return BHS_ERR_INVALID;
     if (!(k > 0.0)) return BHS_ERR_UNSUPPORTED;
-    if (k_im != 0.0 && plan->d != 3) return BHS_ERR_UNSUPPORTED;  // complex wavenumbers: spherical family only
     cudaStream_t st = (cudaStream_t)stream;
     const int d = plan->d, L = plan->n_end, H = plan->H;
     const int64_t npair = (int64_t)L * (L + 1) / 2;

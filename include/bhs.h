@@ -15,8 +15,7 @@
  *   - return value: 0 = ok, <0 = invalid argument (BHS_ERR_*), >0 = cudaError_t of a failed launch;
  *   - coordinate types are the chain trees 'a' (d=2), 'ba' (d=3), 'bba' (d=4): passed as `d`;
  *   - wavenumbers are real arrays `d_k`; an optional `d_k_im` (NULL = real wavenumbers) adds imaginary parts
- *     (absorbing media, Im k != 0).  Complex wavenumbers are implemented for d = 3 (spherical family: h_n by upward
- *     recurrence from closed forms, never as j + i y); for d = 2, 4 they return BHS_ERR_UNSUPPORTED;
+ *     (absorbing media, Im k != 0); h_n^{(1)} is then always computed directly (never as j + i y, which cancels);
  *   - matrices are ROW-major (C order), exactly the reference's [..., B, harm, B', harm'] layout.
  */
 #ifndef BHS_H
@@ -73,6 +72,13 @@ int bhs_plan_coupling_stats(const bhs_plan_t *plan, int64_t *nterms, int64_t *by
  * d_out: complex128 [nx, n_max+1] (imaginary part zero for J and Y). */
 int bhs_bessel(int d, int kind, int derivative, int n_max, const double *d_x, int64_t nx,
                double *d_out, void *stream);
+
+/* Complex argument x = x_re + i x_im != 0 (complex wavenumbers): kind J or H1 only, same layout.  j by Miller's
+ * algorithm normalised on closed forms (spherical) / on e^{-+ix} = J_0 + 2 sum (-+i)^k J_k (cylindrical); h^{(1)} by
+ * upward recurrence from orders 0, 1 (spherical: closed forms; cylindrical: Hankel asymptotics for |x| >= 18,
+ * K_nu(-ix) by Steed's CF2 for Im x > 3, J + iY otherwise). */
+int bhs_bessel_z(int d, int kind, int derivative, int n_max, const double *d_x_re,
+                 const double *d_x_im, int64_t nx, double *d_out, void *stream);
 
 /* K2: orthonormal harmonics in ultrasphere (Phase(0)) order ----------------------------------
  * d_xyz: [d, npts] cartesian points (need not be normalised); d_out: complex128 [npts, H(n_end2)].
