@@ -306,6 +306,10 @@ def run_b200(args) -> None:
 
     # ---- per-kernel split + roofline of the LU trailing update (rank 0, eager profiled pass) -------------
     if rank == 0:
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_zgemm_traffic.json")))
+        except Exception:
+            traffic = {}
         peak_dmma = max(_ops.fp64_peak(1, 4096), 1e-9)
         peak_dfma = max(_ops.fp64_peak(0, 4096), 1e-9)
         nprof = min(4, K)
@@ -337,7 +341,9 @@ def run_b200(args) -> None:
             "achieved": gemm_tf, "peak": peak_dmma, "unit": "TFLOP/s", "frac": gemm_tf / peak_dmma,
             "peak_source": "FP64 mma.sync m8n8k4 register-resident loop measured in this run (bhs_fp64_peak); "
                            "MEASURED_PEAKS.json carries no FP64 figure",
-            "traffic": None,
+            "traffic": traffic.get("traffic_bytes"), "traffic_note": traffic.get("launch", "no ncu capture found")
+            + " -- dram__bytes_read.sum + dram__bytes_write.sum of that one launch (algorithmic bytes of the same launch: "
+            + str(traffic.get("algorithmic_bytes")) + ")",
             "launches": int(g["count"]), "avg_launch_ms": g["ms"] / max(g["count"], 1),
             "flops_per_launch_avg": g["work"] / max(g["count"], 1),
             "scope": "trailing updates of the 128-wide outer blocks (97.7 % of the LU flops), every launch of the "
