@@ -97,3 +97,38 @@ def test_expand_x_false_matches_loop(bhs):
     for i, k in enumerate(ks):
         ref = bo.biem("a", uin=bo.plane_wave(k=k, direction=np.array([1.0, 0.0]))[0], k=k, n_end=9, centers=cen, radii=np.ones(2))
         assert rel(u[:, i], ref.uscat(x[:, :, i])) < TOL
+
+
+def test_batched_geometries_and_per_ball_alpha(bhs):
+    """Leading batch axis on centers / radii (a different geometry per system): identical to a loop of calls.  Per-ball
+    alpha / beta arrays go with a scalar k -- the reference's own shape check (_biem.py:292-306 broadcasts alpha.shape,
+    ball axis included, against k.shape) rejects them together with a batched k, and so does the mirror."""
+    c = bhs.create_from_branching_types("ba")
+    rng = np.random.default_rng(11)
+    K, B, n_end = 3, 2, 7
+    cen = np.stack([np.array([[0.0, 2.0 + 0.3 * i, 0.0], [0.4 * i, -2.0, 0.2]]) for i in range(K)])
+    rad = np.stack([np.array([1.0 - 0.1 * i, 0.8 + 0.1 * i]) for i in range(K)])
+    ks = np.array([0.9, 1.7, 2.6])
+    uin, uin_grad = bhs.plane_wave(k=ks, direction=np.array([[1.0], [0.0], [0.0]]))
+    calc = bhs.biem(c, uin=uin, uin_grad=uin_grad, k=ks, n_end=n_end, eta=np.ones(K), centers=cen, radii=rad, alpha=0.7,
+                    beta=0.2 + 0.1j)
+    assert calc.density.shape == (K, B, n_end * n_end) and calc.matrix.shape == (K, B, n_end * n_end, B, n_end * n_end)
+    x = np.array([[0.0, 5.0], [0.0, 0.5], [0.0, -1.0]])
+    u = calc.uscat(x)
+    for i in range(K):
+        ou, og = bo.plane_wave(k=ks[i], direction=np.array([1.0, 0.0, 0.0]))
+        ref = bo.biem("ba", uin=ou, uin_grad=og, k=ks[i], n_end=n_end, eta=1.0, centers=cen[i], radii=rad[i], alpha=0.7,
+                      beta=0.2 + 0.1j)
+        assert rel(calc.density[i], ref.density) < TOL
+        assert rel(calc.matrix[i], ref.matrix) < TOL
+        assert rel(u[:, i], ref.uscat(x)) < TOL
+    alpha = rng.normal(size=B) + 1j * rng.normal(size=B)
+    beta = rng.normal(size=B) + 1j * rng.normal(size=B)
+    k = np.asarray(1.3)
+    uin, uin_grad = bhs.plane_wave(k=k, direction=np.array([1.0, 0.0, 0.0]))
+    one = bhs.biem(c, uin=uin, uin_grad=uin_grad, k=k, n_end=n_end, centers=cen[1], radii=rad[1], alpha=alpha, beta=beta)
+    ou, og = bo.plane_wave(k=1.3, direction=np.array([1.0, 0.0, 0.0]))
+    ref = bo.biem("ba", uin=ou, uin_grad=og, k=1.3, n_end=n_end, centers=cen[1], radii=rad[1], alpha=alpha, beta=beta)
+    assert rel(one.density, ref.density) < TOL
+    with pytest.raises(ValueError):
+        bhs.biem(c, uin=uin, k=ks, n_end=n_end, eta=np.ones(K), centers=cen, radii=rad, alpha=np.ones((K, B)))
