@@ -368,6 +368,7 @@ class SweepEngine:
         self.al = torch.ones((B,), dtype=C128, device=dev)
         self.be = torch.zeros((B,), dtype=C128, device=dev)
         self.slots = [_Slot(d, n_end, B, self.N) for _ in range(nslots)]
+        self.slot_bytes = nslots * 16 * self.N * self.N
         self.use_graphs = use_graphs
 
     def _body(self, s: _Slot, solve: bool) -> None:
@@ -427,6 +428,7 @@ class SweepEngine:
 
 
 _engines: dict = {}
+_MAX_ENGINES = 4
 
 
 def _sweep_slots(N: int = 0) -> int:
@@ -451,8 +453,16 @@ def _get_engine(d: int, n_end: int, B: int, nslots: int, complex_k: bool = False
     key = (torch.cuda.current_device(), d, n_end, B, nslots, complex_k)
     e = _engines.get(key)
     if e is None:
+        # the slot matrices of cached engines stay allocated: keep the cache small (most recent first, at most
+        # _MAX_ENGINES entries and never more than a quarter of the device memory in total)
+        need = nslots * 16 * (B * get_plan(d, n_end).H) ** 2
+        _, total = torch.cuda.mem_get_info()
+        while _engines and (len(_engines) >= _MAX_ENGINES or need + sum(x.slot_bytes for x in _engines.values()) > total // 4):
+            _engines.pop(next(iter(_engines)))
         e = SweepEngine(d, n_end, B, nslots, complex_k=complex_k)
         _engines[key] = e
+    else:
+        _engines[key] = _engines.pop(key)  # move to the end: most recently used
     return e
 
 

@@ -132,3 +132,21 @@ def test_batched_geometries_and_per_ball_alpha(bhs):
     assert rel(one.density, ref.density) < TOL
     with pytest.raises(ValueError):
         bhs.biem(c, uin=uin, k=ks, n_end=n_end, eta=np.ones(K), centers=cen, radii=rad, alpha=np.ones((K, B)))
+
+
+def test_hand_built_result_record(bhs):
+    """A BIEMResultCalculator assembled by hand (e.g. from a density computed elsewhere) evaluates like the oracle."""
+    c = bhs.create_from_branching_types("ba")
+    cen = np.array([[0.0, 2.0, 0.0], [0.0, -2.0, 0.0], [3.5, 0.0, 1.0]])
+    rad = np.array([1.0, 0.9, 0.6])
+    ref = bo.biem("ba", uin=bo.plane_wave(k=1.9, direction=np.array([0.0, 0.0, 1.0]))[0], k=1.9, n_end=8, eta=0.6,
+                  centers=cen, radii=rad)
+    rec = bhs.BIEMResultCalculator(c=c, centers=cen.T.copy(), radii=rad, k=np.asarray(1.9), n_end=8, eta=np.asarray(0.6),
+                                   kind="outer", density=ref.density)
+    rng = np.random.default_rng(2)
+    x = rng.uniform(-5, 5, size=(3, 4, 6))
+    u, want = rec.uscat(x), ref.uscat(x)
+    ok = ~np.isnan(want)
+    assert u.shape == (4, 6) and np.array_equal(np.isnan(u), ~ok)
+    assert rel(u[ok], want[ok]) < TOL
+    assert rel(rec.uscat(x, per_ball=True)[ok], ref.uscat(x, per_ball=True)[ok]) < TOL
