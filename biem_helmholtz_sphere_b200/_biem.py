@@ -21,6 +21,7 @@ Deliberate differences from the reference (documented in DESIGN.md):
 
 from __future__ import annotations
 
+import contextlib
 import math
 import warnings
 from collections.abc import Callable
@@ -466,6 +467,16 @@ def _get_engine(d: int, n_end: int, B: int, nslots: int, complex_k: bool = False
     return e
 
 
+_side_streams: dict = {}
+
+
+def _uscat_streams(n: int = 8):
+    dev = torch.cuda.current_device()
+    if dev not in _side_streams:
+        _side_streams[dev] = [torch.cuda.Stream(device=dev) for _ in range(n)]
+    return _side_streams[dev]
+
+
 def clear_engines() -> None:
     """Drop cached sweep engines (frees their N x N slot buffers)."""
     _engines.clear()
@@ -723,11 +734,30 @@ def biem_u(res: Any, x: Array, /, far_field: bool = False, per_ball: bool = Fals
     ks_host = st.get("ks_host") or st["ks"].tolist()
     etas_host = st.get("etas_host") or st["etas"].tolist()
     outs = []
+    P_pts = per_sys[0].shape[1] if K else 0
+    # Small point sets (probe points of a sweep) are latency-bound, one CTA each: spread the systems over a few side
+    # streams so that the launches overlap.  Large point sets fill the device on their own.
+    side = _uscat_streams() if (K > 4 and P_pts <= 8192) else None
+    if side:
+        cur = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        for s_ in side:
+            s_.wait_event(ready)
     for i in range(K):
-        o = _ops.uscat(d, n_end, cen_k[i].contiguous(), rad_k[i].contiguous(), ks_host[i], etas_host[i],
-                       dens[i].contiguous(), per_sys[i], far_field=far_field, per_ball=per_ball,
-                       inner=(res.kind == "inner"))
+        ctx = torch.cuda.stream(side[i % len(side)]) if side else contextlib.nullcontext()
+        with ctx:
+            o = _ops.uscat(d, n_end, cen_k[i].contiguous(), rad_k[i].contiguous(), ks_host[i], etas_host[i],
+                           dens[i].contiguous(), per_sys[i], far_field=far_field, per_ball=per_ball,
+                           inner=(res.kind == "inner"))
+        if side:
+            o.record_stream(cur)
         outs.append(o)
+    if side:
+        for s_ in side:
+            done = torch.cuda.Event()
+            done.record(s_)
+            cur.wait_event(done)
     out = torch.stack(outs, dim=1) if nb else outs[0]  # [P, K(, B)] or [P(, B)]
     tail = (B,) if per_ball else ()
     out = out.reshape(xshape + batch_shape + tail)
