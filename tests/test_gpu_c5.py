@@ -71,5 +71,23 @@ def test_c5_full_size():
     assert out["bc_residual_max"] < 1e-7
     assert abs(out["nan_fraction"] - 64 * 3.141592653589793 / 1600.0) < 2e-3
     assert bool(torch.all(torch.isfinite(torch.view_as_real(dens))))
-    print(f"\nC5 full: assemble {out['assemble_ms']:.1f} ms, LU {out['solve_ms']:.0f} ms ({out['lu_tflops']:.1f} TFLOP/s), "
+    # field kernel at the full coefficient size (64 spheres x 576 harmonics) against the oracle's evaluation of the SAME
+    # density on a 40 x 40 sub-grid of the heat map (SURVEY 8d parity gate)
+    from biem_helmholtz_sphere_b200 import _ops
+    from biem_helmholtz_sphere_b200.geometry import field_grid, grid_centers
+    from oracle import biem_oracle as O
+
+    cen = grid_centers(4, 3)
+    x = field_grid(40, 20.0, 3) + 0.0137
+    x[2] = 0.0
+    ref = O.OracleResult(c=O.OracleCoordinates("ba"), centers=cen.T.copy(), radii=np.ones(64), k=1.0, n_end=24, eta=1.0,
+                         kind="outer", density=dens.cpu().numpy(), matrix=None)
+    want = ref.uscat(x)
+    got = _ops.uscat(3, 24, cen, np.ones(64), 1.0, 1.0, dens, x.reshape(3, -1)).cpu().numpy().reshape(40, 40)
+    nan_w = np.isnan(want)
+    assert np.array_equal(nan_w, np.isnan(got))
+    err_u = np.max(np.abs(got[~nan_w] - want[~nan_w])) / np.max(np.abs(want[~nan_w]))
+    assert err_u < 1e-10, err_u
+    print(f"\nC5 full: field kernel vs oracle on a 40x40 sub-grid: rel err {err_u:.1e}")
+    print(f"C5 full: assemble {out['assemble_ms']:.1f} ms, LU {out['solve_ms']:.0f} ms ({out['lu_tflops']:.1f} TFLOP/s), "
           f"residual {out['solve_rel_residual']:.1e}, bc {out['bc_residual_max']:.1e}")
