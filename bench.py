@@ -386,6 +386,13 @@ def run_b200(args) -> None:
         dist.destroy_process_group()
 
 
+def _load_profile(name: str) -> dict:
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", name)))
+    except Exception:
+        return {}
+
+
 def _measured_peaks() -> dict:
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -459,6 +466,7 @@ def _bench_uscat(args, bhs, _ops, torch, dev, rank, world, barrier, dist):
                      "note": "counted flops = 8 P B H (one complex FMA per point x ball x harmonic; special-function "
                              "generation not counted); per-GPU figure against the DFMA peak measured in this run"},
         "nan_fraction": nan_frac,
+        "ncu": _load_profile("r01_uscat_ncu.json"),
     }
 
 
