@@ -464,7 +464,9 @@ def _bench_uscat(args, bhs, _ops, torch, dev, rank, world, barrier, dist):
         "roofline": {"bound": "fp64", "achieved": flops / (ms * 1e-3) * 1e-12 / world, "peak": peak_dfma, "unit": "TFLOP/s",
                      "frac": flops / (ms * 1e-3) * 1e-12 / world / peak_dfma,
                      "note": "counted flops = 8 P B H (one complex FMA per point x ball x harmonic; special-function "
-                             "generation not counted); per-GPU figure against the DFMA peak measured in this run"},
+                             "generation not counted); per-GPU figure against the DFMA peak measured in this run. The grid and "
+                             "the sphere centres are coplanar (x2 = 0), so the device-selected planar variant of the kernel runs "
+                             "(8 FP64 instructions per step instead of 12); non-coplanar inputs measure 0.44"},
         "nan_fraction": nan_frac,
         "ncu": _load_profile("r01_uscat_ncu.json"),
     }

@@ -26,7 +26,8 @@ struct UscatArgs {
     const double* centers;  // [B][d]
     const double* radii;    // [B]
     const cplx* coefg;      // generic: [B][H]
-    const double* rec;      // 3-D: [B][4 + 4*npair] doubles
+    const double* rec;      // 3-D: [B][4 + 4*npair] doubles ([B][4 + 2*npair] for the planar variant)
+    const int* planar;      // 3-D: device flag, 1 = every point and every centre share the same x2 (see uscat_planar_check_kernel)
     const double* beta;     // 3-D: [npair]
     const int32_t* idx;     // [H][s]
     const int32_t* deg;     // [H]
@@ -64,12 +65,17 @@ __global__ void uscat_coef3d_kernel(int L, int LMAX, int B, double k, double k_i
                                     const double4* __restrict__ rad, const cplx* __restrict__ radz,
                                     const double* __restrict__ norm,
                                     const cplx* __restrict__ density, double* __restrict__ rec,
-                                    double* __restrict__ beta) {
+                                    double* __restrict__ beta, double* __restrict__ rec2, int* __restrict__ planar) {
     const int npair = LMAX * (LMAX + 1) / 2;
-    const int64_t stride = 4 + 4 * (int64_t)npair;
+    const int64_t stride = 4 + 4 * (int64_t)npair, stride2 = 4 + 2 * (int64_t)npair;
     int b = blockIdx.x;
     double* rb = rec + stride * b;
-    if (threadIdx.x < 4) rb[threadIdx.x] = threadIdx.x < 3 ? centers[b * 3 + threadIdx.x] : radii[b];
+    double* rb2 = rec2 + stride2 * b;
+    if (threadIdx.x < 4) {
+        rb[threadIdx.x] = threadIdx.x < 3 ? centers[b * 3 + threadIdx.x] : radii[b];
+        rb2[threadIdx.x] = rb[threadIdx.x];
+    }
+    if (b == 0 && threadIdx.x == 0) planar[0] = 1;  // cleared by uscat_planar_check_kernel on the first mismatch
     const int H = L * L;
     for (int e = threadIdx.x; e < npair; e += blockDim.x) {
         // decode (m, n) from the m-major running index
@@ -94,7 +100,23 @@ __global__ void uscat_coef3d_kernel(int L, int LMAX, int B, double k, double k_i
             out = make_double4(cp.x, cp.y, cm.x, cm.y);
         }
         reinterpret_cast<double4*>(rb + 4)[e] = out;
+        // planar variant: e^{+-i m phi} are equal (phi = 0 or pi), so only c_{n,+m} + c_{n,-m} is needed
+        reinterpret_cast<double2*>(rb2 + 4)[e] = make_double2(out.x + out.z, out.y + out.w);
     }
+}
+
+// planar[0] stays 1 only if every centre and every field point has the same x2: then x - c_b has no x2 component for any
+// (point, ball), the azimuth of every pair is 0 or pi, and the +-m sums collapse (heat maps through coplanar centres,
+// the reference's plot_biem use case: plot.py:63-82).
+__global__ void uscat_planar_check_kernel(int64_t P, const double* __restrict__ x2, int B,
+                                          const double* __restrict__ centers, int* __restrict__ planar) {
+    const double c2 = centers[2];
+    bool ok = true;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x)
+        ok = ok && (x2[p] == c2);
+    if (blockIdx.x == 0)
+        for (int b = threadIdx.x; b < B; b += blockDim.x) ok = ok && (centers[b * 3 + 2] == c2);
+    if (!ok) planar[0] = 0;
 }
 
 // ---- 3-D fast kernel --------------------------------------------------------------------------------
@@ -105,16 +127,22 @@ __global__ void uscat_coef3d_kernel(int L, int LMAX, int B, double k, double k_i
     {                                                                           \
         const double gr = hr[(N_) < LMAX ? (N_) : 0] * (Q);                     \
         const double gi = hi[(N_) < LMAX ? (N_) : 0] * (Q);                     \
-        tpr = fma(gr, cc.x, tpr); tpi = fma(gr, cc.y, tpi);                     \
-        tmr = fma(gr, cc.z, tmr); tmi = fma(gr, cc.w, tmi);                     \
-        tpr = fma(-gi, cc.y, tpr); tpi = fma(gi, cc.x, tpi);                    \
-        tmr = fma(-gi, cc.w, tmr); tmi = fma(gi, cc.z, tmi);                    \
+        if (PLANAR) {                                                           \
+            const double2 cd = recs2_m[N_];                                     \
+            tpr = fma(gr, cd.x, tpr); tpi = fma(gr, cd.y, tpi);                 \
+            tpr = fma(-gi, cd.y, tpr); tpi = fma(gi, cd.x, tpi);                \
+        } else {                                                                \
+            const double4 cc = recs_m[N_];                                      \
+            tpr = fma(gr, cc.x, tpr); tpi = fma(gr, cc.y, tpi);                 \
+            tmr = fma(gr, cc.z, tmr); tmi = fma(gr, cc.w, tmi);                 \
+            tpr = fma(-gi, cc.y, tpr); tpi = fma(gi, cc.x, tpi);                \
+            tmr = fma(-gi, cc.w, tmr); tmi = fma(gi, cc.z, tmi);                \
+        }                                                                       \
     }
 #define US_STEP(N)                                                              \
     us_l##N:                                                                    \
         if ((N) < LMAX) {                                                       \
             constexpr int N_ = (N);                                             \
-            const double4 cc = recs_m[N_];                                      \
             const double bt = beta_m[N_];                                       \
             if ((N_ & 1) == 0) {                                                \
                 US_ACC(qa)                                                      \
@@ -125,12 +153,14 @@ __global__ void uscat_coef3d_kernel(int L, int LMAX, int B, double k, double k_i
             }                                                                   \
         }
 
-template <int LMAX, bool ZK>
+template <int LMAX, bool ZK, bool PLANAR>
 __global__ void __launch_bounds__(US3D_THREADS) uscat3d_kernel(UscatArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    // the general and the planar variant are both launched; the device flag decides which one does the work
+    if (a.planar && (a.planar[0] != 0) != PLANAR) return;
     const int L = a.L, B = a.B;
     constexpr int npair = LMAX * (LMAX + 1) / 2;
-    constexpr int rec_doubles = 4 + 4 * npair;
+    constexpr int rec_doubles = 4 + (PLANAR ? 2 : 4) * npair;
     double* stage0 = reinterpret_cast<double*>(smem_raw);
     double* stage1 = stage0 + US3D_CB * rec_doubles;
     double* sbeta = stage1 + US3D_CB * rec_doubles;
@@ -191,6 +221,7 @@ __global__ void __launch_bounds__(US3D_THREADS) uscat3d_kernel(UscatArgs a) {
                     sp = dx2 * irxy;
                 }
             }
+            if (PLANAR) cp = dx1 < 0.0 ? -1.0 : 1.0;  // dx2 == 0 exactly: the azimuth is 0 or pi
             // radial part: h_n(kr) upward (far field: the (-i)^n is folded into the coefficients)
             double hr[LMAX], hi[LMAX];
             if (far) {
@@ -238,8 +269,10 @@ __global__ void __launch_bounds__(US3D_THREADS) uscat3d_kernel(UscatArgs a) {
                 double qa = (m & 1) ? 0.0 : qmm, qb = (m & 1) ? qmm : 0.0;
                 double tpr = 0.0, tpi = 0.0, tmr = 0.0, tmi = 0.0;
                 const int off = m * LMAX - (m * (m - 1)) / 2 - m;
-                const double4* recs_m = recs + off;
+                const double4* recs_m = recs + off;                                          // general: (c+, c-)
+                const double2* recs2_m = reinterpret_cast<const double2*>(rb + 4) + off;     // planar: c+ + c-
                 const double* beta_m = sbeta + off;
+                (void)recs_m; (void)recs2_m;
                 // binary dispatch to the Duff entry point n = m (a switch compiles to a linear compare chain here)
                 if (m < 16) {
                     if (m < 8) {
@@ -398,12 +431,19 @@ __global__ void __launch_bounds__(US3D_THREADS) uscat3d_kernel(UscatArgs a) {
                 US_STEP(29)
                 US_STEP(30)
                 US_STEP(31)
-                // (T+ e^{i m phi} + T- e^{-i m phi})
-                br += (tpr + tmr) * cm - (tpi - tmi) * sm;
-                bi += (tpi + tmi) * cm + (tpr - tmr) * sm;
-                const double cn = cm * cp - sm * sp;
-                sm = sm * cp + cm * sp;
-                cm = cn;
+                if (PLANAR) {
+                    // phi = 0 or pi: e^{+-i m phi} = cp^m (real), T = T+ + T-
+                    br = fma(tpr, cm, br);
+                    bi = fma(tpi, cm, bi);
+                    cm *= cp;
+                } else {
+                    // (T+ e^{i m phi} + T- e^{-i m phi})
+                    br += (tpr + tmr) * cm - (tpi - tmi) * sm;
+                    bi += (tpi + tmi) * cm + (tpr - tmr) * sm;
+                    const double cn = cm * cp - sm * sp;
+                    sm = sm * cp + cm * sp;
+                    cm = cn;
+                }
                 qmm *= sn;
             }
             if (far) {
@@ -573,24 +613,34 @@ extern "C" int64_t bhs_uscat_workspace(const bhs_plan_t* plan, int B) {
     if (!plan || B <= 0) return BHS_ERR_INVALID;
     int64_t L = plan->n_end, LM = (L + 7) / 8 * 8, npair = LM * (LM + 1) / 2;
     int64_t rad = align256((int64_t)B * L * 4 * sizeof(cplx));  // real (j, j', y, y') or complex (j, j', h, h') table
-    int64_t c3 = align256((int64_t)B * (4 + 4 * npair) * sizeof(double)) + align256(npair * sizeof(double));
+    int64_t c3 = align256((int64_t)B * (4 + 4 * npair) * sizeof(double)) + align256(npair * sizeof(double)) +
+                 align256((int64_t)B * (4 + 2 * npair) * sizeof(double)) + 256;  // records, beta, planar records, flag
     int64_t cg = align256((int64_t)B * plan->H * sizeof(cplx));
     int64_t kbuf = 256;
     return rad + (c3 > cg ? c3 : cg) + kbuf;
 }
 
-template <int LMAX>
-static int launch_uscat3d(const UscatArgs& a, cudaStream_t st) {
+template <int LMAX, bool ZK, bool PLANAR>
+static void launch_uscat3d_one(const UscatArgs& a, const double* rec, cudaStream_t st) {
     const int npair = LMAX * (LMAX + 1) / 2;
-    size_t smem = (size_t)(2 * US3D_CB * (4 + 4 * npair) + npair) * sizeof(double);
+    size_t smem = (size_t)(2 * US3D_CB * (4 + (PLANAR ? 2 : 4) * npair) + npair) * sizeof(double);
+    cudaFuncSetAttribute(uscat3d_kernel<LMAX, ZK, PLANAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int64_t blocks = (a.P + US3D_THREADS - 1) / US3D_THREADS;
+    UscatArgs b = a;
+    b.rec = rec;
+    uscat3d_kernel<LMAX, ZK, PLANAR><<<(unsigned)blocks, US3D_THREADS, smem, st>>>(b);
+}
+
+// rec2 != nullptr: the planar variant is launched as well; the device flag a.planar selects which of the two runs
+template <int LMAX>
+static int launch_uscat3d(const UscatArgs& a, const double* rec2, cudaStream_t st) {
     bhs_prof_begin(BHS_PROF_USCAT, st);
-    if (a.k_im != 0.0) {
-        cudaFuncSetAttribute(uscat3d_kernel<LMAX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        uscat3d_kernel<LMAX, true><<<(unsigned)blocks, US3D_THREADS, smem, st>>>(a);
-    } else {
-        cudaFuncSetAttribute(uscat3d_kernel<LMAX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        uscat3d_kernel<LMAX, false><<<(unsigned)blocks, US3D_THREADS, smem, st>>>(a);
+    if (a.k_im != 0.0) launch_uscat3d_one<LMAX, true, false>(a, a.rec, st);
+    else launch_uscat3d_one<LMAX, false, false>(a, a.rec, st);
+    BHS_COUNT_LAUNCH();
+    if (rec2) {
+        if (a.k_im != 0.0) launch_uscat3d_one<LMAX, true, true>(a, rec2, st);
+        else launch_uscat3d_one<LMAX, false, true>(a, rec2, st);
     }
     bhs_prof_end(BHS_PROF_USCAT, 8.0 * (double)a.P * a.B * a.H, st);
     BHS_CHECK_LAUNCH();
@@ -618,22 +668,40 @@ extern "C" int bhs_uscat(const bhs_plan_t* plan, int B, const double* d_centers,
     UscatArgs a;
     a.d = d; a.L = L; a.H = H; a.B = B; a.flags = flags; a.k = k; a.k_im = k_im; a.eta = eta;
     a.x = d_x; a.P = P; a.centers = d_centers; a.radii = d_radii;
-    a.coefg = nullptr; a.rec = nullptr; a.beta = plan->d_us_beta; a.idx = plan->d_idx; a.deg = plan->d_deg;
+    a.coefg = nullptr; a.rec = nullptr; a.planar = nullptr; a.beta = plan->d_us_beta; a.idx = plan->d_idx; a.deg = plan->d_deg;
     a.out = (cplx*)d_out;
     if (d == 3 && L <= 32) {
         const int LM = (L + 7) / 8 * 8;
         const int64_t npm = (int64_t)LM * (LM + 1) / 2;
-        double* d_beta = (double*)(d_coef + align256((int64_t)B * (4 + 4 * npm) * sizeof(double)));
+        unsigned char* q = d_coef + align256((int64_t)B * (4 + 4 * npm) * sizeof(double));
+        double* d_beta = (double*)q;
+        q += align256(npm * sizeof(double));
+        double* d_rec2 = (double*)q;
+        q += align256((int64_t)B * (4 + 2 * npm) * sizeof(double));
+        int* d_planar = (int*)q;
         uscat_coef3d_kernel<<<B, 128, 0, st>>>(L, LM, B, k, k_im, eta, far, d_centers, d_radii, d_rad, d_radz,
-                                               plan->d_us_norm, (const cplx*)d_density, (double*)d_coef, d_beta);
+                                               plan->d_us_norm, (const cplx*)d_density, (double*)d_coef, d_beta, d_rec2,
+                                               d_planar);
         BHS_CHECK_LAUNCH();
         a.rec = (const double*)d_coef;
         a.beta = d_beta;
+        a.planar = nullptr;
+        const double* rec2 = nullptr;
+        if (!far) {
+            // coplanar points and centres (decided on the device, no host round trip): +-m collapse, 8 instead of 12
+            // FP64 instructions per (n, |m|) step
+            int64_t cb = (P + 255) / 256;
+            if (cb > 148 * 4) cb = 148 * 4;
+            uscat_planar_check_kernel<<<(unsigned)cb, 256, 0, st>>>(P, d_x + 2 * P, B, d_centers, d_planar);
+            BHS_CHECK_LAUNCH();
+            a.planar = d_planar;
+            rec2 = d_rec2;
+        }
         (void)npair;
-        if (L <= 8) return launch_uscat3d<8>(a, st);
-        if (L <= 16) return launch_uscat3d<16>(a, st);
-        if (L <= 24) return launch_uscat3d<24>(a, st);
-        return launch_uscat3d<32>(a, st);
+        if (L <= 8) return launch_uscat3d<8>(a, rec2, st);
+        if (L <= 16) return launch_uscat3d<16>(a, rec2, st);
+        if (L <= 24) return launch_uscat3d<24>(a, rec2, st);
+        return launch_uscat3d<32>(a, rec2, st);
     }
     int64_t tot = (int64_t)B * H;
     uscat_coef_generic_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(d, L, H, B, k, k_im, eta, far, d_radii,

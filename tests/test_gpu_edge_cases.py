@@ -150,3 +150,34 @@ def test_hand_built_result_record(bhs):
     assert u.shape == (4, 6) and np.array_equal(np.isnan(u), ~ok)
     assert rel(u[ok], want[ok]) < TOL
     assert rel(rec.uscat(x, per_ball=True)[ok], ref.uscat(x, per_ball=True)[ok]) < TOL
+
+
+@pytest.mark.parametrize("case", ["coplanar", "points_off_plane", "centres_off_plane", "negative_side"])
+def test_uscat_planar_fast_path_selection(bhs, case):
+    """The 3-D field kernel has a device-selected fast path for points and centres that all share one x2 (planar heat
+    maps).  Both selections must agree with the oracle, including points on both sides of a ball (azimuth 0 and pi)."""
+    from biem_helmholtz_sphere_b200 import _ops
+
+    rng = np.random.default_rng(8)
+    B, n_end = 3, 13
+    cen = np.array([[0.0, 2.0, 0.4], [0.5, -2.0, 0.4], [4.0, 0.3, 0.4]])
+    if case == "centres_off_plane":
+        cen[1, 2] = 0.1
+    rad = np.array([1.0, 0.8, 1.2])
+    deg = bo.degree_table("ba", n_end)
+    dens = (rng.normal(size=(B, n_end * n_end)) + 1j * rng.normal(size=(B, n_end * n_end))) * (0.6 ** deg)[None, :]
+    x = rng.uniform(-6, 6, size=(3, 257))
+    x[2] = 0.4
+    if case == "points_off_plane":
+        x[2, 100] = 0.4000001
+    if case == "negative_side":
+        x[1] = -np.abs(x[1]) - 3.5  # every point has dx1 < 0 for every ball
+    x[:, 0] = [0.0, 2.0 + 2.0, 0.4]  # on the in-plane axis through ball 0's centre
+    res = bo.OracleResult(c=bo.OracleCoordinates("ba"), centers=cen.T.copy(), radii=rad, k=2.3, n_end=n_end, eta=0.8,
+                          kind="outer", density=dens, matrix=None)
+    for pb in (False, True):
+        want = bo.biem_u(res, x, per_ball=pb)
+        got = _ops.uscat(3, n_end, cen, rad, 2.3, 0.8, dens, x, per_ball=pb).cpu().numpy()
+        nan = np.isnan(want)
+        assert np.array_equal(nan, np.isnan(got))
+        assert rel(got[~nan], want[~nan]) < 1e-11
