@@ -335,17 +335,19 @@ def point_source(*, k: Array, source: Array, n: int) -> tuple[Callable[[Array], 
 # sweep engine: streams + CUDA graphs around (assemble -> LU solve) for many independent systems
 # --------------------------------------------------------------------------------------------------
 class _Slot:
-    def __init__(self, d: int, n_end: int, B: int, N: int):
+    """Buffers of one group of `S` systems that are assembled and factorised in lock step."""
+
+    def __init__(self, d: int, n_end: int, B: int, N: int, S: int):
         dev = _dev()
         plan = get_plan(d, n_end)
         self.stream = torch.cuda.Stream(device=dev)
-        self.A = torch.empty((N, N), dtype=C128, device=dev)
-        self.k = torch.zeros((1,), dtype=F64, device=dev)
-        self.k_im = torch.zeros((1,), dtype=F64, device=dev)
-        self.eta = torch.ones((1,), dtype=F64, device=dev)
-        self.rhs = torch.zeros((N,), dtype=C128, device=dev)
-        self.bufs = _ops.SolveBuffers(N, 1)
-        self.work = _ops._work(_ops.load().bhs_assemble_workspace(plan.handle, B, 1))
+        self.A = torch.empty((S, N, N), dtype=C128, device=dev)
+        self.k = torch.ones((S,), dtype=F64, device=dev)
+        self.k_im = torch.zeros((S,), dtype=F64, device=dev)
+        self.eta = torch.ones((S,), dtype=F64, device=dev)
+        self.rhs = torch.zeros((S, N), dtype=C128, device=dev)
+        self.bufs = _ops.SolveBuffers(N, 1, S)
+        self.work = _ops._work(_ops.load().bhs_assemble_workspace(plan.handle, B, S))
         self.graph: torch.cuda.CUDAGraph | None = None
         self.warm = False
 
@@ -353,14 +355,19 @@ class _Slot:
 class SweepEngine:
     """Assemble + solve many independent systems that share one geometry (different k / eta / rhs).
 
-    Each of ``nslots`` slots owns a stream, an N x N matrix buffer and a CUDA graph of the whole
-    (assembly kernels -> LU kernels) sequence, so independent systems overlap on the device and the host
-    issues one graph launch per system.  Nothing here synchronises with the host.
+    Systems are processed in groups of ``batch``: one launch of every assembly / LU kernel handles the whole group
+    (bhs_assemble with nsys = batch, bhs_zgesv_batched), which divides the number of launches -- and of CUDA-graph nodes
+    -- per system by ``batch``.  ``nslots`` groups are in flight at a time, each on its own stream with its own buffers and
+    a CUDA graph of the (assembly -> LU) sequence, so that the latency-bound panel steps of one group overlap the
+    tensor-core updates of the others.  A last, partial group is padded with the slot's previous wavenumbers (their results
+    are discarded).  Nothing here synchronises with the host.
     """
 
-    def __init__(self, d: int, n_end: int, B: int, nslots: int = 3, use_graphs: bool = True, complex_k: bool = False):
+    def __init__(self, d: int, n_end: int, B: int, nslots: int = 3, use_graphs: bool = True, complex_k: bool = False,
+                 batch: int = 1):
         self.d, self.n_end, self.B = d, n_end, B
         self.complex_k = complex_k
+        self.batch = batch
         self.plan = get_plan(d, n_end)
         self.N = B * self.plan.H
         dev = _dev()
@@ -368,15 +375,17 @@ class SweepEngine:
         self.rad = torch.ones((B,), dtype=F64, device=dev)
         self.al = torch.ones((B,), dtype=C128, device=dev)
         self.be = torch.zeros((B,), dtype=C128, device=dev)
-        self.slots = [_Slot(d, n_end, B, self.N) for _ in range(nslots)]
-        self.slot_bytes = nslots * 16 * self.N * self.N
+        self.slots = [_Slot(d, n_end, B, self.N, batch) for _ in range(nslots)]
+        self.slot_bytes = nslots * batch * 16 * self.N * self.N
         self.use_graphs = use_graphs
 
-    def _body(self, s: _Slot, solve: bool) -> None:
-        _ops.assemble(self.d, self.n_end, self.cen, self.rad, s.k, s.eta, self.al, self.be, out=s.A[None], work=s.work,
+    def _assemble(self, s: _Slot) -> None:
+        _ops.assemble(self.d, self.n_end, self.cen, self.rad, s.k, s.eta, self.al, self.be, out=s.A, work=s.work,
                       k_im=s.k_im if self.complex_k else None)
-        if solve:
-            _ops.zgesv_(s.A, s.rhs, s.bufs)
+
+    def _body(self, s: _Slot) -> None:
+        self._assemble(s)
+        _ops.zgesv_batched_(s.A, s.rhs, s.bufs)
 
     def set_geometry(self, cen, rad, al, be) -> None:
         self.cen.copy_(cen)
@@ -387,41 +396,42 @@ class SweepEngine:
     def run(self, ks, etas, f_hat, out_density, out_matrix=None, kis=None) -> None:
         """ks, etas (and kis = Im k for a complex_k engine): [K]; f_hat: [K, N]; out_density: [K, N]; out_matrix: [K, N, N] or None."""
         K = ks.shape[0]
+        S = self.batch
         cur = torch.cuda.current_stream()
         ready = torch.cuda.Event()
         ready.record(cur)
         for s in self.slots:
             s.stream.wait_event(ready)
-        for i in range(K):
-            s = self.slots[i % len(self.slots)]
+        for g_i, i0 in enumerate(range(0, K, S)):
+            n = min(S, K - i0)
+            s = self.slots[g_i % len(self.slots)]
             with torch.cuda.stream(s.stream):
-                s.k.copy_(ks[i : i + 1], non_blocking=True)
+                s.k[:n].copy_(ks[i0 : i0 + n], non_blocking=True)
                 if self.complex_k:
-                    s.k_im.copy_(kis[i : i + 1], non_blocking=True)
-                s.eta.copy_(etas[i : i + 1], non_blocking=True)
-                s.rhs.copy_(f_hat[i], non_blocking=True)
+                    s.k_im[:n].copy_(kis[i0 : i0 + n], non_blocking=True)
+                s.eta[:n].copy_(etas[i0 : i0 + n], non_blocking=True)
+                s.rhs[:n].copy_(f_hat[i0 : i0 + n], non_blocking=True)
                 if out_matrix is not None:
-                    # the caller keeps the matrix: assemble, copy out, then factor the slot copy
-                    _ops.assemble(self.d, self.n_end, self.cen, self.rad, s.k, s.eta, self.al, self.be, out=s.A[None],
-                                  work=s.work, k_im=s.k_im if self.complex_k else None)
-                    out_matrix[i].copy_(s.A, non_blocking=True)
-                    _ops.zgesv_(s.A, s.rhs, s.bufs)
+                    # the caller keeps the matrices: assemble, copy out, then factor the slot copies
+                    self._assemble(s)
+                    out_matrix[i0 : i0 + n].copy_(s.A[:n], non_blocking=True)
+                    _ops.zgesv_batched_(s.A, s.rhs, s.bufs)
                 elif not self.use_graphs:
-                    self._body(s, True)
+                    self._body(s)
                 elif s.graph is not None:
                     s.graph.replay()
                 elif not s.warm:
-                    self._body(s, True)  # first use of the slot: eager run, which also warms every kernel up
+                    self._body(s)  # first use of the slot: eager run, which also warms every kernel up
                     s.warm = True
                 else:
                     # second use (in this or a later sweep): capture the (assembly -> LU) sequence once, then replay
                     s.stream.synchronize()
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g, stream=s.stream):
-                        self._body(s, True)
+                        self._body(s)
                     s.graph = g
                     g.replay()
-                out_density[i].copy_(s.rhs, non_blocking=True)
+                out_density[i0 : i0 + n].copy_(s.rhs[:n], non_blocking=True)
         for s in self.slots:
             done = torch.cuda.Event()
             done.record(s.stream)
@@ -432,35 +442,41 @@ _engines: dict = {}
 _MAX_ENGINES = 4
 
 
-def _sweep_slots(N: int = 0) -> int:
-    """Independent systems kept in flight by a sweep (each owns a stream, an N x N buffer and a CUDA graph).
+def _sweep_shape(N: int, K: int) -> tuple[int, int]:
+    """(batch, nslots) of a sweep of K systems with N unknowns each: `batch` systems per launch, `nslots` such groups in
+    flight (each group owns a stream, batch N x N buffers and a CUDA graph).
 
-    The LU panel steps are latency-bound, so throughput comes from overlapping many systems: measured on B200 at
-    N = 4096, 3 / 12 / 32 slots give 54 / 106 / 132 systems/s.  Default 32, capped so that the slot matrices use
-    at most a quarter of the free device memory; override with BHS_SWEEP_SLOTS."""
+    The LU panel steps are latency-bound, so throughput comes from keeping many systems in flight.  Measured on B200 at
+    N = 4096 (systems/s): 1 x 3 / 1 x 12 / 1 x 32 (batch x groups) -> 54 / 106 / 142; 8 x 4 -> 134, 4 x 8 -> 138,
+    2 x 16 -> 142, 8 x 8 -> 144, 4 x 16 -> 146, 2 x 32 -> 147: independent streams matter more than fewer launches.
+    Defaults: batch 2, 32 groups (64 systems in flight); capped so that the buffers use at most a quarter of the free
+    device memory.  Override with BHS_SWEEP_BATCH / BHS_SWEEP_SLOTS."""
     import os
 
+    if K <= 1 or N > 12000:
+        return 1, 1
+    batch = max(1, int(os.environ.get("BHS_SWEEP_BATCH", "2")))
+    batch = min(batch, K)
+    free, _ = torch.cuda.mem_get_info()
+    fit = max(1, int(free // 4 // (16 * N * N)))  # systems that fit
+    batch = max(1, min(batch, fit))
     env = os.environ.get("BHS_SWEEP_SLOTS")
-    if env:
-        return max(1, int(env))
-    slots = 32
-    if N > 0:
-        free, _ = torch.cuda.mem_get_info()
-        slots = max(1, min(slots, int(free // 4 // (16 * N * N))))
-    return slots
+    nslots = max(1, int(env)) if env else max(1, 64 // batch)
+    nslots = max(1, min(nslots, -(-K // batch), fit // batch))
+    return batch, nslots
 
 
-def _get_engine(d: int, n_end: int, B: int, nslots: int, complex_k: bool = False) -> SweepEngine:
-    key = (torch.cuda.current_device(), d, n_end, B, nslots, complex_k)
+def _get_engine(d: int, n_end: int, B: int, nslots: int, complex_k: bool = False, batch: int = 1) -> SweepEngine:
+    key = (torch.cuda.current_device(), d, n_end, B, nslots, complex_k, batch)
     e = _engines.get(key)
     if e is None:
         # the slot matrices of cached engines stay allocated: keep the cache small (most recent first, at most
         # _MAX_ENGINES entries and never more than a quarter of the device memory in total)
-        need = nslots * 16 * (B * get_plan(d, n_end).H) ** 2
+        need = nslots * batch * 16 * (B * get_plan(d, n_end).H) ** 2
         _, total = torch.cuda.mem_get_info()
         while _engines and (len(_engines) >= _MAX_ENGINES or need + sum(x.slot_bytes for x in _engines.values()) > total // 4):
             _engines.pop(next(iter(_engines)))
-        e = SweepEngine(d, n_end, B, nslots, complex_k=complex_k)
+        e = SweepEngine(d, n_end, B, nslots, complex_k=complex_k, batch=batch)
         _engines[key] = e
     else:
         _engines[key] = _engines.pop(key)  # move to the end: most recently used
@@ -643,8 +659,8 @@ def biem(
             matrix_t = torch.empty((K, N, N), dtype=C128, device=_dev()) if keep_matrix else None
             rhs = f_hat.reshape(K, N)
             if shared_geom:
-                nslots = 1 if (K == 1 or N > 12000) else min(_sweep_slots(N), K)
-                eng = _get_engine(d, n_end, B, nslots, complex_k=kis is not None)
+                batch, nslots = _sweep_shape(N, K)
+                eng = _get_engine(d, n_end, B, nslots, complex_k=kis is not None, batch=batch)
                 eng.set_geometry(*geom(0))
                 eng.run(ks, ets, rhs, density_t, matrix_t, kis=kis)
             else:

@@ -37,6 +37,8 @@ SIGNATURES = {
     "bhs_diag_coef": (i32, [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "bhs_zgesv_workspace": (i64, [i64, i32]),
     "bhs_zgesv": (i32, [i64, i32, vp, i64, vp, vp, vp, vp, vp]),
+    "bhs_zgesv_batched_workspace": (i64, [i64, i32, i32]),
+    "bhs_zgesv_batched": (i32, [i64, i32, i32, vp, i64, i64, vp, i64, vp, vp, vp, vp]),
     "bhs_zgetrf": (i32, [i64, vp, i64, vp, vp, vp, vp]),
     "bhs_zgetrs": (i32, [i64, i32, vp, i64, vp, vp, vp, vp]),
     "bhs_zgemm_workspace": (i64, [i64, i64, i64]),

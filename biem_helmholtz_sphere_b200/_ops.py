@@ -125,14 +125,15 @@ def diag_coef(d: int, n_end: int, radii, k, eta=None, alpha=None, beta=None, k_i
 
 
 class SolveBuffers:
-    """Reusable ipiv / info / workspace of bhs_zgesv for one system size."""
+    """Reusable ipiv / info / workspace of bhs_zgesv (or bhs_zgesv_batched with nbatch systems) for one system size."""
 
-    def __init__(self, N: int, nrhs: int = 1):
+    def __init__(self, N: int, nrhs: int = 1, nbatch: int = 1):
         dev = _dev()
         self.N = N
-        self.ipiv = torch.empty((N,), dtype=torch.int32, device=dev)
-        self.info = torch.zeros((1,), dtype=torch.int32, device=dev)
-        self.work = _work(load().bhs_zgesv_workspace(N, nrhs))
+        self.nbatch = nbatch
+        self.ipiv = torch.empty((nbatch * N,), dtype=torch.int32, device=dev)
+        self.info = torch.zeros((nbatch,), dtype=torch.int32, device=dev)
+        self.work = _work(load().bhs_zgesv_batched_workspace(N, nrhs, nbatch))
 
 
 def zgesv_(A: torch.Tensor, rhs: torch.Tensor, bufs: SolveBuffers | None = None):
@@ -145,6 +146,20 @@ def zgesv_(A: torch.Tensor, rhs: torch.Tensor, bufs: SolveBuffers | None = None)
         bufs = SolveBuffers(N, nrhs)
     check(load().bhs_zgesv(N, nrhs, ptr(A), A.stride(0), ptr(rhs), ptr(bufs.ipiv), ptr(bufs.info), ptr(bufs.work),
                            stream_ptr()), "bhs_zgesv")
+    return rhs, bufs
+
+
+def zgesv_batched_(A: torch.Tensor, rhs: torch.Tensor, bufs: SolveBuffers | None = None):
+    """In-place solve of S independent systems in lock step: A [S, N, N] (overwritten by the factors), rhs [S, N] or
+    [S, N, nrhs] (overwritten by the solutions)   (bhs_zgesv_batched)."""
+    S, N = A.shape[0], A.shape[1]
+    assert A.dtype == C128 and A.is_cuda and A.stride(2) == 1 and rhs.dtype == C128 and rhs.is_contiguous()
+    nrhs = 1 if rhs.dim() == 2 else rhs.shape[2]
+    if bufs is None:
+        bufs = SolveBuffers(N, nrhs, S)
+    assert bufs.nbatch >= S
+    check(load().bhs_zgesv_batched(N, nrhs, S, ptr(A), A.stride(1), A.stride(0), ptr(rhs), rhs.stride(0), ptr(bufs.ipiv),
+                                   ptr(bufs.info), ptr(bufs.work), stream_ptr()), "bhs_zgesv_batched")
     return rhs, bufs
 
 

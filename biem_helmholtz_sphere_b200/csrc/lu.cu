@@ -30,6 +30,19 @@
 static inline int64_t al256(int64_t v) { return (v + 255) & ~(int64_t)255; }
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// Batched factorisation: every kernel of this file handles `nbatch` independent systems of one size in lock step, system
+// z = blockIdx.z, so that a k-sweep issues one launch per step for a whole group of systems.  Per-system strides
+// (in elements of the respective array):
+struct LuBatch {
+    int64_t sA;     // matrix (complex)
+    int64_t sRhs;   // right-hand sides (complex)
+    int64_t sIpiv;  // pivots (int32)
+    int64_t sCand;  // tournament candidate lists (int32)
+    int64_t sDblk;  // factored diagonal block scratch (complex)
+    int64_t sLp;    // packed L image (double)
+    int64_t sUp;    // packed U image (double)
+};
+
 // =====================================================================================================
 // GEMM:  C[rows, cols] -= Lp * Up
 // =====================================================================================================
@@ -43,6 +56,7 @@ struct GemmArgs {
     int64_t row_base, col_base;  // global row / col of packed tile (0, 0)
     int rt0, ct0;                // first row / col tile of this launch
     int64_t row_lo, row_hi, col_lo, col_hi;  // output window (global indices, half open)
+    int64_t sC, sLp, sUp;                    // per-system strides (blockIdx.z)
 };
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
@@ -59,8 +73,9 @@ __global__ void __launch_bounds__(G_THREADS, 2) zgemm_sub_kernel(GemmArgs g) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 1, wn = warp & 1;
     const int rt = g.rt0 + blockIdx.y, ct = g.ct0 + blockIdx.x;
-    const double* Lt = g.Lp + ((int64_t)rt * g.nks_total + g.ks0) * G_A_STAGE;
-    const double* Ut = g.Up + ((int64_t)ct * g.nks_total + g.ks0) * G_B_STAGE;
+    g.C += (int64_t)blockIdx.z * g.sC;
+    const double* Lt = g.Lp + (int64_t)blockIdx.z * g.sLp + ((int64_t)rt * g.nks_total + g.ks0) * G_A_STAGE;
+    const double* Ut = g.Up + (int64_t)blockIdx.z * g.sUp + ((int64_t)ct * g.nks_total + g.ks0) * G_B_STAGE;
     if (tid == 0) {
         for (int s = 0; s < G_STAGES; ++s) mbar_init(&full[s], 1);
         mbar_fence_init();
@@ -135,7 +150,9 @@ static const size_t G_SMEM = (size_t)G_STAGES * (G_A_STAGE + G_B_STAGE) * sizeof
 // Lp tile (rt, stage): [64 rows][20] doubles, row r = interleaved complex A[row_base + 64 rt + r][k0 + 8 stage ..]
 __global__ void pack_l_kernel(const cplx* __restrict__ A, int64_t ld, int64_t N, int64_t row_base, int64_t r_begin,
                               int64_t r_end_pad, int64_t k0, int K, int Kpad, double* __restrict__ Lp, int nks_total,
-                              int ks_off) {
+                              int ks_off, int64_t sA, int64_t sLp) {
+    A += (int64_t)blockIdx.z * sA;
+    Lp += (int64_t)blockIdx.z * sLp;
     // thread -> (row, kc); kc fastest
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t nrows = r_end_pad - r_begin;
@@ -153,7 +170,9 @@ __global__ void pack_l_kernel(const cplx* __restrict__ A, int64_t ld, int64_t N,
 // Up tile (ct, stage): [128 real cols][20] doubles: row 2j: (-br, +bi) pairs, row 2j+1: (-bi, -br)
 __global__ void pack_u_kernel(const cplx* __restrict__ A, int64_t ld, int64_t ncols_total, int64_t k_row0, int K,
                               int Kpad, int64_t c_begin, int64_t c_end_pad, double* __restrict__ Up, int nks_total,
-                              int ks_off) {
+                              int ks_off, int64_t sA, int64_t sUp) {
+    A += (int64_t)blockIdx.z * sA;
+    Up += (int64_t)blockIdx.z * sUp;
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t ncols = c_end_pad - c_begin;
     if (idx >= ncols * Kpad) return;
@@ -204,7 +223,15 @@ __device__ __forceinline__ cplx crecip_fast(cplx p) {
 __global__ void __launch_bounds__(LU_R) lu_select_kernel(const cplx* __restrict__ A, int64_t ld, int64_t col0, int w,
                                                          const int32_t* __restrict__ rows_in, int64_t n_in,
                                                          int64_t row_begin, int64_t row_end,
-                                                         int32_t* __restrict__ rows_out, SelectFinal fin) {
+                                                         int32_t* __restrict__ rows_out, SelectFinal fin, LuBatch bs) {
+    A += (int64_t)blockIdx.z * bs.sA;
+    if (rows_in) rows_in += (int64_t)blockIdx.z * bs.sCand;
+    rows_out += (int64_t)blockIdx.z * bs.sCand;
+    if (fin.ipiv) {
+        fin.ipiv += (int64_t)blockIdx.z * bs.sIpiv;
+        fin.info += blockIdx.z;
+        fin.dblk += (int64_t)blockIdx.z * bs.sDblk;
+    }
     constexpr int NW = LU_R / 32;
     __shared__ cplx prow[2][NW][LU_NB];
     __shared__ cplx prinv[2][NW];
@@ -309,7 +336,10 @@ __global__ void __launch_bounds__(LU_R) lu_select_kernel(const cplx* __restrict_
 // With `dblk` (matrix only) the panel's own columns [j, j+w) of rows [j, j+w) then receive the factored diagonal
 // block produced by the last tournament round.
 __global__ void lu_swap_kernel(cplx* __restrict__ M, int64_t ld, int64_t ncols, const int32_t* __restrict__ ipiv,
-                               int64_t j, int w, const cplx* __restrict__ dblk) {
+                               int64_t j, int w, const cplx* __restrict__ dblk, int64_t sM, int64_t sIpiv, int64_t sDblk) {
+    M += (int64_t)blockIdx.z * sM;
+    ipiv += (int64_t)blockIdx.z * sIpiv;
+    if (dblk) dblk += (int64_t)blockIdx.z * sDblk;
     int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncols) return;
     for (int q = 0; q < w; ++q) {
@@ -326,7 +356,9 @@ __global__ void lu_swap_kernel(cplx* __restrict__ M, int64_t ld, int64_t ncols, 
 
 // L21 = A21 U11^{-1}: one row per thread (registers), U11 in shared memory.  Also emits the packed
 // GEMM image of the new L columns (rows below the diagonal block).
-__global__ void __launch_bounds__(LU_R) lu_l21_kernel(cplx* __restrict__ A, int64_t ld, int64_t N, int64_t j, int w) {
+__global__ void __launch_bounds__(LU_R) lu_l21_kernel(cplx* __restrict__ A, int64_t ld, int64_t N, int64_t j, int w,
+                                                      int64_t sA) {
+    A += (int64_t)blockIdx.z * sA;
     __shared__ cplx U[LU_NB][LU_NB + 1];
     __shared__ cplx rdiag[LU_NB];
     const int tid = threadIdx.x;
@@ -364,7 +396,9 @@ __global__ void __launch_bounds__(LU_R) lu_l21_kernel(cplx* __restrict__ A, int6
 // U12 = L11^{-1} A12 for a 32-row block: one column per thread (registers), L11 (unit lower) in smem.
 __global__ void __launch_bounds__(128) lu_trsm32_kernel(cplx* __restrict__ A, int64_t ld, int64_t j, int w,
                                                         cplx* __restrict__ X, int64_t ldx, int64_t c_begin,
-                                                        int64_t c_end) {
+                                                        int64_t c_end, int64_t sA) {
+    A += (int64_t)blockIdx.z * sA;
+    X += (int64_t)blockIdx.z * sA;
     __shared__ cplx Ls[LU_NB][LU_NB + 1];
     const int tid = threadIdx.x;
     for (int e = tid; e < LU_NB * LU_NB; e += 128) {
@@ -395,7 +429,9 @@ __global__ void __launch_bounds__(128) lu_trsm32_kernel(cplx* __restrict__ A, in
 // rhs[r, :] -= sum_{q<K} M[r, k0+q] * rhs[k0+q, :]   for r in [r_begin, r_end): one warp per row
 __global__ void __launch_bounds__(256) rhs_gemv_sub_kernel(const cplx* __restrict__ M, int64_t ld, int64_t r_begin,
                                                            int64_t r_end, int64_t k0, int K, cplx* __restrict__ rhs,
-                                                           int nrhs) {
+                                                           int nrhs, int64_t sA, int64_t sRhs) {
+    M += (int64_t)blockIdx.z * sA;
+    rhs += (int64_t)blockIdx.z * sRhs;
     const int lane = threadIdx.x & 31;
     int64_t r = r_begin + (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (r >= r_end) return;
@@ -418,7 +454,10 @@ __global__ void __launch_bounds__(256) rhs_gemv_sub_kernel(const cplx* __restric
 }
 // Solve the T x T diagonal block at k0 against rhs rows [k0, k0+T): lower-unit (forward) or upper (backward).
 __global__ void __launch_bounds__(128) rhs_block_solve_kernel(const cplx* __restrict__ M, int64_t ld, int64_t k0, int T,
-                                                              int upper, cplx* __restrict__ rhs, int nrhs) {
+                                                              int upper, cplx* __restrict__ rhs, int nrhs, int64_t sA,
+                                                              int64_t sRhs) {
+    M += (int64_t)blockIdx.z * sA;
+    rhs += (int64_t)blockIdx.z * sRhs;
     __shared__ cplx v[LU_NBO];
     const int tid = threadIdx.x;
     for (int c = 0; c < nrhs; ++c) {
@@ -477,6 +516,8 @@ struct LuCtx {
     double* Up;
     int nks_total;      // LU_NBO / G_KC
     int64_t J;          // current outer block start (anchor of Lp rows and of the stage index)
+    int nbatch;         // systems factorised in lock step (grid z)
+    LuBatch bs;
     cudaStream_t st;
     int err;
 };
@@ -487,21 +528,24 @@ struct LuWork {
     cplx* dblk;
     double* Lp;
     double* Up;
+    int64_t ncand, sLp, sUp;
     int64_t bytes;
 };
-static LuWork lu_carve(int64_t N, void* base) {
+static LuWork lu_carve(int64_t N, int nbatch, void* base) {
     LuWork w;
     unsigned char* c = (unsigned char*)base;
     int64_t off = 0;
     auto take = [&](int64_t b) { unsigned char* r = c + off; off += al256(b); return r; };
-    int64_t ncand = cdiv64(N, LU_R) * LU_NB + LU_NB;
-    w.cand0 = (int32_t*)take(ncand * 4);
-    w.cand1 = (int32_t*)take(ncand * 4);
-    w.dblk = (cplx*)take((int64_t)LU_NB * LU_NB * sizeof(cplx));
+    w.ncand = cdiv64(N, LU_R) * LU_NB + LU_NB;
+    w.cand0 = (int32_t*)take(w.ncand * 4 * nbatch);
+    w.cand1 = (int32_t*)take(w.ncand * 4 * nbatch);
+    w.dblk = (cplx*)take((int64_t)LU_NB * LU_NB * sizeof(cplx) * nbatch);
     int64_t rtiles = cdiv64(N, G_TM) + 1, ctiles = cdiv64(N, G_TN) + 1;
     int nks = LU_NBO / G_KC;
-    w.Lp = (double*)take(rtiles * nks * G_A_STAGE * 8);
-    w.Up = (double*)take(ctiles * nks * G_B_STAGE * 8);
+    w.sLp = rtiles * nks * G_A_STAGE;
+    w.sUp = ctiles * nks * G_B_STAGE;
+    w.Lp = (double*)take(w.sLp * 8 * nbatch);
+    w.Up = (double*)take(w.sUp * 8 * nbatch);
     w.bytes = off;
     return w;
 }
@@ -530,11 +574,12 @@ static void lu_gemm(LuCtx& x, int64_t r_lo, int64_t r_hi, int64_t c_lo, int64_t 
     g.ct0 = (int)(c_lo / G_TN);
     int rt1 = (int)((r_hi - 1 - x.J) / G_TM), ct1 = (int)((c_hi - 1) / G_TN);
     g.row_lo = r_lo; g.row_hi = r_hi; g.col_lo = c_lo; g.col_hi = c_hi;
-    dim3 grid(ct1 - g.ct0 + 1, rt1 - g.rt0 + 1);
+    g.sC = x.bs.sA; g.sLp = x.bs.sLp; g.sUp = x.bs.sUp;
+    dim3 grid(ct1 - g.ct0 + 1, rt1 - g.rt0 + 1, x.nbatch);
     const int pcat = (K >= LU_NBO || (k0 == x.J && r_lo >= x.J + LU_NBO)) ? BHS_PROF_LU_GEMM : BHS_PROF_LU_GEMM_IN;
     bhs_prof_begin(pcat, x.st);
     zgemm_sub_kernel<<<grid, G_THREADS, G_SMEM, x.st>>>(g);
-    bhs_prof_end(pcat, 8.0 * (double)(r_hi - r_lo) * (double)(c_hi - c_lo) * (double)K, x.st);
+    bhs_prof_end(pcat, 8.0 * (double)(r_hi - r_lo) * (double)(c_hi - c_lo) * (double)K * x.nbatch, x.st);
     LU_LAUNCH_CHECK(x);
 }
 static void lu_pack_l(LuCtx& x, int64_t r_lo, int64_t r_hi, int64_t k0, int K) {
@@ -544,8 +589,8 @@ static void lu_pack_l(LuCtx& x, int64_t r_lo, int64_t r_hi, int64_t k0, int K) {
     int Kpad = ((K + G_KC - 1) / G_KC) * G_KC;
     int64_t tot = (r_end_pad - r_lo) * Kpad;
     bhs_prof_begin(BHS_PROF_LU_PACK, x.st);
-    pack_l_kernel<<<(unsigned)cdiv64(tot, 256), 256, 0, x.st>>>(x.A, x.ld, x.N, x.J, r_lo, r_end_pad, k0, K, Kpad, x.Lp,
-                                                               x.nks_total, (int)((k0 - x.J) / G_KC));
+    pack_l_kernel<<<dim3((unsigned)cdiv64(tot, 256), 1, x.nbatch), 256, 0, x.st>>>(
+        x.A, x.ld, x.N, x.J, r_lo, r_end_pad, k0, K, Kpad, x.Lp, x.nks_total, (int)((k0 - x.J) / G_KC), x.bs.sA, x.bs.sLp);
     bhs_prof_end(BHS_PROF_LU_PACK, 0.0, x.st);
     LU_LAUNCH_CHECK(x);
 }
@@ -555,8 +600,8 @@ static void lu_pack_u(LuCtx& x, int64_t k0, int K, int64_t c_lo, int64_t c_hi) {
     int Kpad = ((K + G_KC - 1) / G_KC) * G_KC;
     int64_t tot = (c_end_pad - c_begin) * Kpad;
     bhs_prof_begin(BHS_PROF_LU_PACK, x.st);
-    pack_u_kernel<<<(unsigned)cdiv64(tot, 256), 256, 0, x.st>>>(x.A, x.ld, x.N, k0, K, Kpad, c_begin, c_end_pad, x.Up,
-                                                               x.nks_total, (int)((k0 - x.J) / G_KC));
+    pack_u_kernel<<<dim3((unsigned)cdiv64(tot, 256), 1, x.nbatch), 256, 0, x.st>>>(
+        x.A, x.ld, x.N, k0, K, Kpad, c_begin, c_end_pad, x.Up, x.nks_total, (int)((k0 - x.J) / G_KC), x.bs.sA, x.bs.sUp);
     bhs_prof_end(BHS_PROF_LU_PACK, 0.0, x.st);
     LU_LAUNCH_CHECK(x);
 }
@@ -568,26 +613,28 @@ static void lu_panel(LuCtx& x, int64_t j, int w) {
     int cur = 0;
     bhs_prof_begin(BHS_PROF_LU_PANEL, x.st);
     const SelectFinal fin{j, x.ipiv, x.info, x.dblk}, nofin{0, nullptr, nullptr, nullptr};
-    lu_select_kernel<<<(unsigned)nsets, LU_R, 0, x.st>>>(x.A, x.ld, j, w, nullptr, 0, j, x.N, x.cand[cur],
-                                                         nsets == 1 ? fin : nofin);
+    lu_select_kernel<<<dim3((unsigned)nsets, 1, x.nbatch), LU_R, 0, x.st>>>(x.A, x.ld, j, w, nullptr, 0, j, x.N, x.cand[cur],
+                                                                            nsets == 1 ? fin : nofin, x.bs);
     LU_LAUNCH_CHECK(x);
     while (nsets > 1) {
         int64_t n_in = nsets * LU_NB;
         int64_t nsets2 = cdiv64(n_in, LU_R);
-        lu_select_kernel<<<(unsigned)nsets2, LU_R, 0, x.st>>>(x.A, x.ld, j, w, x.cand[cur], n_in, 0, 0, x.cand[cur ^ 1],
-                                                              nsets2 == 1 ? fin : nofin);
+        lu_select_kernel<<<dim3((unsigned)nsets2, 1, x.nbatch), LU_R, 0, x.st>>>(x.A, x.ld, j, w, x.cand[cur], n_in, 0, 0,
+                                                                                 x.cand[cur ^ 1], nsets2 == 1 ? fin : nofin, x.bs);
         LU_LAUNCH_CHECK(x);
         cur ^= 1;
         nsets = nsets2;
     }
-    lu_swap_kernel<<<(unsigned)cdiv64(x.N, 256), 256, 0, x.st>>>(x.A, x.ld, x.N, x.ipiv, j, w, x.dblk);
+    lu_swap_kernel<<<dim3((unsigned)cdiv64(x.N, 256), 1, x.nbatch), 256, 0, x.st>>>(x.A, x.ld, x.N, x.ipiv, j, w, x.dblk, x.bs.sA,
+                                                                                    x.bs.sIpiv, x.bs.sDblk);
     LU_LAUNCH_CHECK(x);
     if (x.rhs) {
-        lu_swap_kernel<<<(unsigned)cdiv64(x.nrhs, 32), 32, 0, x.st>>>(x.rhs, x.nrhs, x.nrhs, x.ipiv, j, w, nullptr);
+        lu_swap_kernel<<<dim3((unsigned)cdiv64(x.nrhs, 32), 1, x.nbatch), 32, 0, x.st>>>(x.rhs, x.nrhs, x.nrhs, x.ipiv, j, w, nullptr,
+                                                                                         x.bs.sRhs, x.bs.sIpiv, 0);
         LU_LAUNCH_CHECK(x);
     }
     if (j + w < x.N) {
-        lu_l21_kernel<<<(unsigned)cdiv64(x.N - j - w, LU_R), LU_R, 0, x.st>>>(x.A, x.ld, x.N, j, w);
+        lu_l21_kernel<<<dim3((unsigned)cdiv64(x.N - j - w, LU_R), 1, x.nbatch), LU_R, 0, x.st>>>(x.A, x.ld, x.N, j, w, x.bs.sA);
         LU_LAUNCH_CHECK(x);
     }
     bhs_prof_end(BHS_PROF_LU_PANEL, 0.0, x.st);
@@ -598,7 +645,8 @@ static void lu_trsm(LuCtx& x, int64_t j0, int T, int64_t c_lo, int64_t c_hi) {
     if (c_lo >= c_hi || T <= 0) return;
     if (T <= LU_NB) {
         bhs_prof_begin(BHS_PROF_LU_TRSM, x.st);
-        lu_trsm32_kernel<<<(unsigned)cdiv64(c_hi - c_lo, 128), 128, 0, x.st>>>(x.A, x.ld, j0, T, x.A, x.ld, c_lo, c_hi);
+        lu_trsm32_kernel<<<dim3((unsigned)cdiv64(c_hi - c_lo, 128), 1, x.nbatch), 128, 0, x.st>>>(x.A, x.ld, j0, T, x.A, x.ld, c_lo,
+                                                                                                  c_hi, x.bs.sA);
         bhs_prof_end(BHS_PROF_LU_TRSM, 0.0, x.st);
         LU_LAUNCH_CHECK(x);
         lu_pack_u(x, j0, T, c_lo, c_hi);
@@ -624,7 +672,7 @@ static void lu_rec(LuCtx& x, int64_t j0, int w) {
 }
 
 static int lu_factor(LuCtx& x) {
-    cudaMemsetAsync(x.info, 0, sizeof(int32_t), x.st);
+    cudaMemsetAsync(x.info, 0, sizeof(int32_t) * x.nbatch, x.st);
     cudaFuncSetAttribute(zgemm_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
     // BHS_LU_GEMM_ONLY=1 (measurement aid, wrong results): issue only the trailing updates, to see how much of a
     // sweep's time the DMMA kernel accounts for on its own
@@ -643,11 +691,11 @@ static int lu_factor(LuCtx& x) {
         if (x.rhs) {
             // forward substitution of this block row: y_J = L11^{-1} rhs_J ; rhs_below -= L21 y_J
             bhs_prof_begin(BHS_PROF_LU_RHS, x.st);
-            rhs_block_solve_kernel<<<1, 128, 0, x.st>>>(x.A, x.ld, J, w, 0, x.rhs, x.nrhs);
+            rhs_block_solve_kernel<<<dim3(1, 1, x.nbatch), 128, 0, x.st>>>(x.A, x.ld, J, w, 0, x.rhs, x.nrhs, x.bs.sA, x.bs.sRhs);
             LU_LAUNCH_CHECK(x);
             if (J + w < x.N) {
-                rhs_gemv_sub_kernel<<<(unsigned)cdiv64(x.N - J - w, 8), 256, 0, x.st>>>(x.A, x.ld, J + w, x.N, J, w, x.rhs,
-                                                                                      x.nrhs);
+                rhs_gemv_sub_kernel<<<dim3((unsigned)cdiv64(x.N - J - w, 8), 1, x.nbatch), 256, 0, x.st>>>(
+                    x.A, x.ld, J + w, x.N, J, w, x.rhs, x.nrhs, x.bs.sA, x.bs.sRhs);
                 LU_LAUNCH_CHECK(x);
             }
             bhs_prof_end(BHS_PROF_LU_RHS, 0.0, x.st);
@@ -667,10 +715,11 @@ static int lu_backward(LuCtx& x) {
     for (int64_t bi = nblk - 1; bi >= 0; --bi) {
         int64_t J = bi * LU_NBO;
         int w = (int)((x.N - J < LU_NBO) ? (x.N - J) : LU_NBO);
-        rhs_block_solve_kernel<<<1, 128, 0, x.st>>>(x.A, x.ld, J, w, 1, x.rhs, x.nrhs);
+        rhs_block_solve_kernel<<<dim3(1, 1, x.nbatch), 128, 0, x.st>>>(x.A, x.ld, J, w, 1, x.rhs, x.nrhs, x.bs.sA, x.bs.sRhs);
         LU_LAUNCH_CHECK(x);
         if (J > 0) {
-            rhs_gemv_sub_kernel<<<(unsigned)cdiv64(J, 8), 256, 0, x.st>>>(x.A, x.ld, 0, J, J, w, x.rhs, x.nrhs);
+            rhs_gemv_sub_kernel<<<dim3((unsigned)cdiv64(J, 8), 1, x.nbatch), 256, 0, x.st>>>(x.A, x.ld, 0, J, J, w, x.rhs, x.nrhs,
+                                                                                         x.bs.sA, x.bs.sRhs);
             LU_LAUNCH_CHECK(x);
         }
     }
@@ -680,14 +729,22 @@ static int lu_backward(LuCtx& x) {
 
 extern "C" int64_t bhs_zgesv_workspace(int64_t N, int nrhs) {
     if (N <= 0 || nrhs < 0) return BHS_ERR_INVALID;
-    return lu_carve(N, nullptr).bytes;
+    return lu_carve(N, 1, nullptr).bytes;
+}
+extern "C" int64_t bhs_zgesv_batched_workspace(int64_t N, int nrhs, int nbatch) {
+    if (N <= 0 || nrhs < 0 || nbatch <= 0) return BHS_ERR_INVALID;
+    return lu_carve(N, nbatch, nullptr).bytes;
 }
 
 static int lu_setup(LuCtx& x, int64_t N, double* d_A, int64_t ld, double* d_rhs, int nrhs, int32_t* d_ipiv,
-                    int32_t* d_info, void* d_work, void* stream) {
-    if (N <= 0 || !d_A || ld < N || !d_ipiv || !d_info || !d_work) return BHS_ERR_INVALID;
+                    int32_t* d_info, void* d_work, void* stream, int nbatch = 1, int64_t strideA = 0,
+                    int64_t stride_rhs = 0) {
+    if (N <= 0 || !d_A || ld < N || !d_ipiv || !d_info || !d_work || nbatch <= 0 || nbatch > 65535) return BHS_ERR_INVALID;
     if (N > 2000000000LL / LU_NB) return BHS_ERR_UNSUPPORTED;
-    LuWork w = lu_carve(N, d_work);
+    LuWork w = lu_carve(N, nbatch, d_work);
+    x.nbatch = nbatch;
+    x.bs.sA = strideA; x.bs.sRhs = stride_rhs; x.bs.sIpiv = N; x.bs.sCand = w.ncand;
+    x.bs.sDblk = (int64_t)LU_NB * LU_NB; x.bs.sLp = w.sLp; x.bs.sUp = w.sUp;
     x.A = (cplx*)d_A; x.ld = ld; x.N = N; x.rhs = (cplx*)d_rhs; x.nrhs = nrhs;
     x.ipiv = d_ipiv; x.info = d_info; x.cand[0] = w.cand0; x.cand[1] = w.cand1; x.dblk = w.dblk;
     x.Lp = w.Lp; x.Up = w.Up; x.nks_total = LU_NBO / G_KC; x.J = 0;
@@ -714,21 +771,36 @@ extern "C" int bhs_zgesv(int64_t N, int nrhs, double* d_A, int64_t ld, double* d
     return lu_backward(x);
 }
 
+// nbatch systems of one size in lock step: A [nbatch][N, ld] (strideA complex elements apart), rhs [nbatch][N, nrhs]
+// (stride_rhs apart), ipiv [nbatch][N], info [nbatch]; workspace bhs_zgesv_batched_workspace.
+extern "C" int bhs_zgesv_batched(int64_t N, int nrhs, int nbatch, double* d_A, int64_t ld, int64_t strideA, double* d_rhs,
+                                 int64_t stride_rhs, int32_t* d_ipiv, int32_t* d_info, void* d_work, void* stream) {
+    if (nrhs <= 0 || !d_rhs || strideA < N * ld - (ld - N) || stride_rhs < N * nrhs) return BHS_ERR_INVALID;
+    LuCtx x;
+    int rc = lu_setup(x, N, d_A, ld, d_rhs, nrhs, d_ipiv, d_info, d_work, stream, nbatch, strideA, stride_rhs);
+    if (rc) return rc;
+    rc = lu_factor(x);
+    if (rc) return rc;
+    return lu_backward(x);
+}
+
 extern "C" int bhs_zgetrs(int64_t N, int nrhs, const double* d_LU, int64_t ld, const int32_t* d_ipiv, double* d_rhs,
                           void* d_work, void* stream) {
     if (N <= 0 || nrhs <= 0 || !d_LU || ld < N || !d_ipiv || !d_rhs) return BHS_ERR_INVALID;
     (void)d_work;
     LuCtx x;
     x.A = (cplx*)d_LU; x.ld = ld; x.N = N; x.rhs = (cplx*)d_rhs; x.nrhs = nrhs;
+    x.nbatch = 1;
+    x.bs = LuBatch{0, 0, 0, 0, 0, 0, 0};
     x.st = (cudaStream_t)stream; x.err = 0;
     rhs_apply_ipiv_kernel<<<1, 32, 0, x.st>>>(d_ipiv, N, x.rhs, nrhs);
     LU_LAUNCH_CHECK(x);
     for (int64_t J = 0; J < N; J += LU_NBO) {
         int w = (int)((N - J < LU_NBO) ? (N - J) : LU_NBO);
-        rhs_block_solve_kernel<<<1, 128, 0, x.st>>>(x.A, ld, J, w, 0, x.rhs, nrhs);
+        rhs_block_solve_kernel<<<1, 128, 0, x.st>>>(x.A, ld, J, w, 0, x.rhs, nrhs, 0, 0);
         LU_LAUNCH_CHECK(x);
         if (J + w < N) {
-            rhs_gemv_sub_kernel<<<(unsigned)cdiv64(N - J - w, 8), 256, 0, x.st>>>(x.A, ld, J + w, N, J, w, x.rhs, nrhs);
+            rhs_gemv_sub_kernel<<<(unsigned)cdiv64(N - J - w, 8), 256, 0, x.st>>>(x.A, ld, J + w, N, J, w, x.rhs, nrhs, 0, 0);
             LU_LAUNCH_CHECK(x);
         }
     }
@@ -753,16 +825,17 @@ extern "C" int bhs_zgemm_sub(int64_t M, int64_t N, int64_t K, const double* d_A,
     double* Up = (double*)((unsigned char*)d_work + al256(cdiv64(M, G_TM) * nks * G_A_STAGE * 8));
     int64_t r_end_pad = cdiv64(M, G_TM) * G_TM, c_end_pad = cdiv64(N, G_TN) * G_TN;
     pack_l_kernel<<<(unsigned)cdiv64(r_end_pad * Kpad, 256), 256, 0, st>>>((const cplx*)d_A, lda, M, 0, 0, r_end_pad, 0, (int)K,
-                                                                        Kpad, Lp, (int)nks, 0);
+                                                                        Kpad, Lp, (int)nks, 0, 0, 0);
     BHS_CHECK_LAUNCH();
     pack_u_kernel<<<(unsigned)cdiv64(c_end_pad * Kpad, 256), 256, 0, st>>>((const cplx*)d_B, ldb, N, 0, (int)K, Kpad, 0,
-                                                                        c_end_pad, Up, (int)nks, 0);
+                                                                        c_end_pad, Up, (int)nks, 0, 0, 0);
     BHS_CHECK_LAUNCH();
     cudaFuncSetAttribute(zgemm_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
     GemmArgs g;
     g.Lp = Lp; g.Up = Up; g.nks_total = (int)nks; g.ks0 = 0; g.nks = (int)nks;
     g.C = (cplx*)d_C; g.ldc = ldc; g.row_base = 0; g.col_base = 0; g.rt0 = 0; g.ct0 = 0;
     g.row_lo = 0; g.row_hi = M; g.col_lo = 0; g.col_hi = N;
+    g.sC = 0; g.sLp = 0; g.sUp = 0;
     dim3 grid((unsigned)cdiv64(N, G_TN), (unsigned)cdiv64(M, G_TM));
     zgemm_sub_kernel<<<grid, G_THREADS, G_SMEM, st>>>(g);
     BHS_CHECK_LAUNCH();

@@ -123,6 +123,13 @@ int bhs_diag_coef(const bhs_plan_t *plan, int B, int nsys, const double *d_radii
 int64_t bhs_zgesv_workspace(int64_t N, int nrhs);
 int bhs_zgesv(int64_t N, int nrhs, double *d_A, int64_t ld, double *d_rhs, int32_t *d_ipiv,
               int32_t *d_info, void *d_work, void *stream);
+/* The same for `nbatch` systems of one size in lock step (one launch per step for the whole group: what a wavenumber
+ * sweep issues).  A [nbatch][N, ld] with strideA complex elements between systems, rhs [nbatch][N, nrhs] stride_rhs apart,
+ * d_ipiv int32 [nbatch][N], d_info int32 [nbatch]. */
+int64_t bhs_zgesv_batched_workspace(int64_t N, int nrhs, int nbatch);
+int bhs_zgesv_batched(int64_t N, int nrhs, int nbatch, double *d_A, int64_t ld, int64_t strideA,
+                      double *d_rhs, int64_t stride_rhs, int32_t *d_ipiv, int32_t *d_info, void *d_work,
+                      void *stream);
 /* The pieces, exposed for tests and for re-solving with stored factors. */
 int bhs_zgetrf(int64_t N, double *d_A, int64_t ld, int32_t *d_ipiv, int32_t *d_info, void *d_work,
                void *stream);

@@ -193,6 +193,31 @@ def test_zgesv_random(ops, N):
     assert err < 1e-8  # random matrices are not well conditioned; the residual is the real check
 
 
+@pytest.mark.parametrize("N,S,nrhs", [(33, 3, 1), (200, 5, 2), (515, 4, 1), (1024, 8, 1)])
+def test_zgesv_batched_equals_single(ops, N, S, nrhs):
+    """bhs_zgesv_batched (S systems in lock step, system index in blockIdx.z) against S separate bhs_zgesv calls: the
+    same kernels run on the same data, so the results must be bit-identical; systems get different pivot orders
+    (rows of system s are scaled / permuted differently)."""
+    import torch
+
+    g = torch.Generator(device="cuda").manual_seed(100 + N)
+    A = torch.randn(S, N, N, dtype=torch.complex128, device="cuda", generator=g)
+    for s_ in range(S):
+        A[s_] = A[s_][torch.randperm(N, device="cuda", generator=g)] * (10.0 ** (s_ - 2))
+    b = torch.randn((S, N) if nrhs == 1 else (S, N, nrhs), dtype=torch.complex128, device="cuda", generator=g)
+    xb, bufs = ops.zgesv_batched_(A.clone(), b.clone())
+    torch.cuda.synchronize()
+    assert bool(torch.all(bufs.info == 0))
+    for s_ in range(S):
+        x1, b1 = ops.zgesv_(A[s_].clone(), b[s_].clone())
+        assert torch.equal(xb[s_], x1), f"system {s_} differs from the single-system solve"
+        assert torch.equal(bufs.ipiv[s_ * N:(s_ + 1) * N], b1.ipiv)
+        rhs_s = b[s_] if nrhs > 1 else b[s_][:, None]
+        xs = xb[s_] if nrhs > 1 else xb[s_][:, None]
+        res = float((A[s_] @ xs - rhs_s).abs().max() / (A[s_].abs().max() * xs.abs().max() * N))
+        assert res < 1e-14
+
+
 def test_zgesv_needs_pivoting(ops):
     import torch
 
