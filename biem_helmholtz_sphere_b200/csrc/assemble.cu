@@ -43,18 +43,26 @@ __global__ void pair_vectors_kernel(int d, int B, const double* __restrict__ cen
 // contraction is done once per DISTINCT t and the result is scaled and written for every pair that shares it.
 // rep[i] = smallest pair index with bit-identical t (exact comparison: irregular geometries simply get U = np - B).
 __global__ void pair_rep_kernel(int d, int B, int dedupe, const double* __restrict__ tv, int32_t* __restrict__ rep) {
+    extern __shared__ __align__(16) double s_tv[];  // [d][np] when it fits (use_smem), else the scan reads global memory
     const int np = B * B;
+    const bool use_smem = dedupe && (size_t)np * d * sizeof(double) <= 96 * 1024;
+    if (use_smem) {
+        for (int e = threadIdx.x; e < np * d; e += blockDim.x) s_tv[e] = tv[e];
+        __syncthreads();
+    }
+    const double* T = use_smem ? s_tv : tv;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= np) return;
     if (i / B == i % B) { rep[i] = -1; return; }
     if (!dedupe) { rep[i] = i; return; }
     double t[BHS_MAX_NODES + 2];
-    for (int a = 0; a < d; ++a) t[a] = tv[(int64_t)a * np + i];
+    for (int a = 0; a < d; ++a) t[a] = T[(int64_t)a * np + i];
     int r = i;
     for (int j = 0; j < i; ++j) {
+        if (T[j] != t[0]) continue;  // first component differs (the diagonal pairs carry a dummy direction: checked below)
         if (j / B == j % B) continue;
         bool same = true;
-        for (int a = 0; a < d; ++a) same = same && (tv[(int64_t)a * np + j] == t[a]);
+        for (int a = 1; a < d; ++a) same = same && (T[(int64_t)a * np + j] == t[a]);
         if (same) { r = j; break; }
     }
     rep[i] = r;
@@ -507,7 +515,13 @@ extern "C" int bhs_assemble(const bhs_plan_t* plan, int B, int nsys, const doubl
         BHS_CHECK_LAUNCH();
     }
     // the search is O(np^2) in the worst case (no duplicates): bounded by skipping it for more than 128 spheres
-    pair_rep_kernel<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(plan->d, B, B <= 128 ? 1 : 0, w.tv, w.rep);
+    {
+        const int dedupe = B <= 128 ? 1 : 0;
+        size_t sm = (size_t)np * plan->d * sizeof(double);
+        if (!dedupe || sm > 96 * 1024) sm = 0;
+        if (sm > 48 * 1024) cudaFuncSetAttribute(pair_rep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        pair_rep_kernel<<<(unsigned)((np + 127) / 128), 128, sm, st>>>(plan->d, B, dedupe, w.tv, w.rep);
+    }
     BHS_CHECK_LAUNCH();
     pair_group_kernel<<<1, 1024, 0, st>>>(B, w.rep, w.uid, w.cursor, w.n_unique, w.grp_rep, w.grp_start, w.members);
     BHS_CHECK_LAUNCH();
