@@ -360,9 +360,23 @@ def run_b200(args) -> None:
         out["lu"] = {"tflops": (8.0 / 3.0) * N ** 3 / (lu_ms / nprof * 1e-3) * 1e-12 if lu_ms > 0 else None,
                      "ms": lu_ms / nprof, "fp64_dmma_peak_tflops": peak_dmma, "fp64_dfma_peak_tflops": peak_dfma}
         hbm = _measured_peaks().get("hbm_gbs", 6650.0)
+        # the assembly kernel only WRITES (16 N^2 bytes): also measure the pure write stream of this device (fill of 4 GiB)
+        wbuf = torch.empty(1 << 30, dtype=torch.int32, device=dev)
+        wbest = 0.0
+        for _ in range(6):
+            w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            w0.record()
+            wbuf.fill_(1)
+            w1.record()
+            torch.cuda.synchronize()
+            wbest = max(wbest, wbuf.numel() * 4 / (w0.elapsed_time(w1) * 1e-3) * 1e-9)
+        del wbuf
         if am["ms"] > 0:
-            out["assembly"] = {"gbs": am["work"] / (am["ms"] * 1e-3) * 1e-9, "ms": am["ms"] / nprof,
-                               "hbm_peak_gbs": hbm, "frac_hbm": am["work"] / (am["ms"] * 1e-3) * 1e-9 / hbm}
+            gbs = am["work"] / (am["ms"] * 1e-3) * 1e-9
+            out["assembly"] = {"gbs": gbs, "ms": am["ms"] / nprof, "hbm_peak_gbs": hbm, "frac_hbm": gbs / hbm,
+                               "write_stream_gbs": wbest, "frac_write_stream": gbs / wbest,
+                               "note": "hbm_peak_gbs is MEASURED_PEAKS.json's copy figure (read + write bytes); "
+                                       "write_stream_gbs is a 4 GiB fill measured in this run"}
         del A, work, bufs
 
     # ---- u_scat points/s on the C5 field grid (64 spheres, n_end = 24), field rows split over the ranks -----

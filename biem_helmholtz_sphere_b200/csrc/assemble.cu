@@ -16,6 +16,7 @@
 #include "special.cuh"
 
 #define ASM_THREADS 256
+#define ASM_EPT (BHS_TILE_E / ASM_THREADS)  // tile entries per thread
 #define ASM_LAYER_COEF (BHS_TILE_E * 8)
 #define ASM_LAYER_IDX (BHS_TILE_E * 2)
 
@@ -310,12 +311,16 @@ __global__ void __launch_bounds__(ASM_THREADS) assemble_kernel(AsmArgs a) {
         mbar_wait(&bar, phase);
         phase ^= 1;
     }
-    // this thread's two entries
-    const int e0 = tid, e1 = tid + ASM_THREADS;
-    const int r0 = e0 / BHS_TILE_C, c0 = e0 % BHS_TILE_C, r1 = e1 / BHS_TILE_C, c1 = e1 % BHS_TILE_C;
-    const int h0 = tr * BHS_TILE_R + r0, hp0 = tc * BHS_TILE_C + c0;
-    const int h1 = tr * BHS_TILE_R + r1, hp1 = tc * BHS_TILE_C + c1;
-    const bool ok0 = h0 < a.H && hp0 < a.H, ok1 = h1 < a.H && hp1 < a.H;
+    // this thread's entries of the tile (ASM_EPT of them, ASM_THREADS apart: a warp covers 32 consecutive columns of a row)
+    int h_[ASM_EPT], hp_[ASM_EPT];
+    bool ok_[ASM_EPT];
+#pragma unroll
+    for (int q = 0; q < ASM_EPT; ++q) {
+        const int e = tid + q * ASM_THREADS;
+        h_[q] = tr * BHS_TILE_R + e / BHS_TILE_C;
+        hp_[q] = tc * BHS_TILE_C + e % BHS_TILE_C;
+        ok_[q] = h_[q] < a.H && hp_[q] < a.H;
+    }
     const int64_t npairs = (int64_t)a.B * a.B;
     cplx* Asys = a.A + (int64_t)sys * a.sys_stride;
     const cplx* rowf = a.rowf + (int64_t)sys * a.B * a.H;
@@ -332,7 +337,9 @@ __global__ void __launch_bounds__(ASM_THREADS) assemble_kernel(AsmArgs a) {
         if (!a.sy_global)
             for (int j = tid; j < hd.sy_cnt; j += ASM_THREADS) s_sy[j] = cmul(y2[j], hpw[dg[j]]);
         __syncthreads();
-        double ar0 = 0.0, ai0 = 0.0, ar1 = 0.0, ai1 = 0.0;
+        double ar[ASM_EPT], ai[ASM_EPT];
+#pragma unroll
+        for (int q = 0; q < ASM_EPT; ++q) { ar[q] = 0.0; ai[q] = 0.0; }
         for (int t0 = 0; t0 < nt; t0 += nt_res) {
             const int tn = min(nt_res, nt - t0);
             if (!resident) {
@@ -347,29 +354,25 @@ __global__ void __launch_bounds__(ASM_THREADS) assemble_kernel(AsmArgs a) {
             }
 #pragma unroll 4
             for (int t = 0; t < tn; ++t) {
-                const double cf0 = s_coef[t * BHS_TILE_E + e0], cf1 = s_coef[t * BHS_TILE_E + e1];
-                const int i0 = s_idx[t * BHS_TILE_E + e0], i1 = s_idx[t * BHS_TILE_E + e1];
-                cplx s0, s1;
-                if (a.sy_global) {
-                    s0 = cmul(y2[i0], hpw[dg[i0]]);
-                    s1 = cmul(y2[i1], hpw[dg[i1]]);
-                } else {
-                    s0 = s_sy[i0];
-                    s1 = s_sy[i1];
+#pragma unroll
+                for (int q = 0; q < ASM_EPT; ++q) {
+                    const int e = tid + q * ASM_THREADS;
+                    const double cf = s_coef[t * BHS_TILE_E + e];
+                    const int ix = s_idx[t * BHS_TILE_E + e];
+                    const cplx sv = a.sy_global ? cmul(y2[ix], hpw[dg[ix]]) : s_sy[ix];
+                    ar[q] = fma(cf, sv.x, ar[q]);
+                    ai[q] = fma(cf, sv.y, ai[q]);
                 }
-                ar0 = fma(cf0, s0.x, ar0); ai0 = fma(cf0, s0.y, ai0);
-                ar1 = fma(cf1, s1.x, ar1); ai1 = fma(cf1, s1.y, ai1);
             }
             if (!resident) __syncthreads();  // everyone done with the chunk before it is overwritten
         }
-        const cplx raw0 = cmake(ar0, ai0), raw1 = cmake(ar1, ai1);
         // Write phase: every pair that shares this translation gets the block, scaled by its own row / column factors.
         // Members are handled four at a time with all factor loads issued before the first store (the loop is
         // otherwise a chain of dependent global-memory latencies).
         const int q_end = a.grp_start[u + 1];
         for (int q0 = a.grp_start[u]; q0 < q_end; q0 += 4) {
             int bb[4], bq[4];
-            cplx rf0[4], rf1[4], cf0[4], cf1[4];
+            cplx rf[4][ASM_EPT], cf[4][ASM_EPT];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int pk = (q0 + i < q_end) ? __ldg(a.members + q0 + i) : -1;
@@ -379,14 +382,21 @@ __global__ void __launch_bounds__(ASM_THREADS) assemble_kernel(AsmArgs a) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 if (bb[i] < 0) continue;
-                if (ok0) { rf0[i] = __ldg(rowf + (int64_t)bb[i] * a.H + h0); cf0[i] = __ldg(colf + (int64_t)bq[i] * a.H + hp0); }
-                if (ok1) { rf1[i] = __ldg(rowf + (int64_t)bb[i] * a.H + h1); cf1[i] = __ldg(colf + (int64_t)bq[i] * a.H + hp1); }
+#pragma unroll
+                for (int q = 0; q < ASM_EPT; ++q)
+                    if (ok_[q]) {
+                        rf[i][q] = __ldg(rowf + (int64_t)bb[i] * a.H + h_[q]);
+                        cf[i][q] = __ldg(colf + (int64_t)bq[i] * a.H + hp_[q]);
+                    }
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 if (bb[i] < 0) continue;
-                if (ok0) Asys[((int64_t)bb[i] * a.H + h0) * a.ld + (int64_t)bq[i] * a.H + hp0] = cmul(cmul(raw0, rf0[i]), cf0[i]);
-                if (ok1) Asys[((int64_t)bb[i] * a.H + h1) * a.ld + (int64_t)bq[i] * a.H + hp1] = cmul(cmul(raw1, rf1[i]), cf1[i]);
+#pragma unroll
+                for (int q = 0; q < ASM_EPT; ++q)
+                    if (ok_[q])
+                        Asys[((int64_t)bb[i] * a.H + h_[q]) * a.ld + (int64_t)bq[i] * a.H + hp_[q]] =
+                            cmul(cmul(cmake(ar[q], ai[q]), rf[i][q]), cf[i][q]);
             }
         }
         __syncthreads();  // s_sy reuse
@@ -545,8 +555,8 @@ extern "C" int bhs_assemble(const bhs_plan_t* plan, int B, int nsys, const doubl
     cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int ntiles = plan->tiles_r * plan->tiles_c;
     // The number of distinct translations U is only known on the device: the y-dimension strides over them, sized
-    // for about four waves of CTAs (2 resident per SM) and never more than the off-diagonal pair count.
-    int64_t chunks = (4 * 2 * 148 + (int64_t)ntiles * nsys - 1) / ((int64_t)ntiles * nsys);
+    // for about four waves of CTAs (4 resident per SM) and never more than the off-diagonal pair count.
+    int64_t chunks = (4 * 4 * 148 + (int64_t)ntiles * nsys - 1) / ((int64_t)ntiles * nsys);
     if (chunks < 1) chunks = 1;
     if (chunks > np - B) chunks = np - B > 0 ? np - B : 1;
     if (chunks > 65535 || nsys > 65535) return BHS_ERR_UNSUPPORTED;

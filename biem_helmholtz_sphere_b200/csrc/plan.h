@@ -11,7 +11,7 @@
 
 // coupling-table tile geometry used by bhs_assemble (rows = harmonic h of the ROW ball b,
 // columns = harmonic h' of the COLUMN ball b')
-#define BHS_TILE_R 8
+#define BHS_TILE_R 4
 #define BHS_TILE_C 64
 #define BHS_TILE_E (BHS_TILE_R * BHS_TILE_C)
 
