@@ -543,7 +543,7 @@ extern "C" int bhs_assemble(const bhs_plan_t* plan, int B, int nsys, const doubl
     a.A = (cplx*)d_A; a.ld = ld; a.sys_stride = sys_stride;
     // shared-memory budget: SY window (worst case H2 entries) + resident coefficient layers
     const size_t budget = 200 * 1024;
-    size_t sy_bytes = ((size_t)plan->H2 * sizeof(cplx) + 127) & ~(size_t)127;
+    size_t sy_bytes = ((size_t)plan->max_sy_cnt * sizeof(cplx) + 127) & ~(size_t)127;  // largest window of any tile
     a.sy_global = 0;
     if (sy_bytes + (ASM_LAYER_COEF + ASM_LAYER_IDX) > budget) {
         a.sy_global = 1;

@@ -197,6 +197,7 @@ static int build_coupling(bhs_plan* p) {
         std::vector<double> coef(ntile * BHS_TILE_E, 0.0);
         std::vector<uint16_t> cidx(ntile * BHS_TILE_E, 0);
         p->max_nt = 1;
+        p->max_sy_cnt = 1;
         for (int tr = 0; tr < p->tiles_r; ++tr)
             for (int tc = 0; tc < p->tiles_c; ++tc) {
                 const size_t ti = (size_t)tr * p->tiles_c + tc;
@@ -213,6 +214,7 @@ static int build_coupling(bhs_plan* p) {
                 if (hi < 0) { lo = 0; hi = 0; }
                 if (hi - lo > 65535) return BHS_ERR_UNSUPPORTED;
                 hd.nt = 1; hd.sy_lo = lo; hd.sy_cnt = hi - lo + 1; hd.pad = 0;
+                p->max_sy_cnt = std::max(p->max_sy_cnt, hd.sy_cnt);
                 hd.coef_off = (int64_t)(ti * BHS_TILE_E);
                 hd.idx_off = (int64_t)(ti * BHS_TILE_E);
                 for (int r = 0; r < BHS_TILE_R; ++r)
@@ -293,6 +295,7 @@ static int build_coupling(bhs_plan* p) {
     std::vector<double> coef;
     std::vector<uint16_t> cidx;
     p->max_nt = 0;
+    p->max_sy_cnt = 1;
     for (int tr = 0; tr < p->tiles_r; ++tr)
         for (int tc = 0; tc < p->tiles_c; ++tc) {
             bhs_tile_hdr& hd = p->h_tiles[(size_t)tr * p->tiles_c + tc];
@@ -309,6 +312,7 @@ static int build_coupling(bhs_plan* p) {
             hd.nt = nt;
             hd.sy_lo = lo;
             hd.sy_cnt = hi - lo + 1;
+            p->max_sy_cnt = std::max(p->max_sy_cnt, hd.sy_cnt);
             hd.pad = 0;
             hd.coef_off = (int64_t)coef.size();
             hd.idx_off = (int64_t)cidx.size();

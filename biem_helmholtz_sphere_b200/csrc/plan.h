@@ -35,6 +35,7 @@ struct bhs_plan {
     std::vector<double> h_qw;     // [Q]
     int64_t coupling_terms, coupling_bytes;
     int tiles_r, tiles_c, max_nt;
+    int max_sy_cnt;  // largest S window (hd.sy_cnt) referenced by one tile: sizes the shared-memory S buffer
     // device tables
     int32_t* d_idx;    // [H][s_ndim]
     int32_t* d_idx2;   // [H2][s_ndim]
