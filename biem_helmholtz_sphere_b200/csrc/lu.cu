@@ -452,39 +452,60 @@ __global__ void __launch_bounds__(256) rhs_gemv_sub_kernel(const cplx* __restric
         }
     }
 }
-// Solve the T x T diagonal block at k0 against rhs rows [k0, k0+T): lower-unit (forward) or upper (backward).
+// Solve the T x T (T <= 128) diagonal block at k0 against rhs rows [k0, k0+T): lower-unit (forward) or upper (backward).
+// The block is staged in shared memory 64 columns at a time (column-major, so that step q reads one contiguous column),
+// instead of every step fetching a strided column from global memory: 128 dependent L2 latencies become 2 bulk loads.
+#define RS_CH 64
 __global__ void __launch_bounds__(128) rhs_block_solve_kernel(const cplx* __restrict__ M, int64_t ld, int64_t k0, int T,
                                                               int upper, cplx* __restrict__ rhs, int nrhs, int64_t sA,
                                                               int64_t sRhs) {
     M += (int64_t)blockIdx.z * sA;
     rhs += (int64_t)blockIdx.z * sRhs;
+    extern __shared__ __align__(16) cplx s_blk[];  // [RS_CH][LU_NBO + 1]
     __shared__ cplx v[LU_NBO];
+    __shared__ cplx rd[RS_CH];
     const int tid = threadIdx.x;
+    constexpr int LDB = LU_NBO + 1;
     for (int c = 0; c < nrhs; ++c) {
         if (tid < T) v[tid] = rhs[(k0 + tid) * nrhs + c];
-        __syncthreads();
-        if (!upper) {
-            for (int q = 0; q < T; ++q) {
-                cplx xq = v[q];
-                if (tid > q && tid < T) v[tid] = cfma(cmake(-M[(k0 + tid) * ld + k0 + q].x, -M[(k0 + tid) * ld + k0 + q].y), xq, v[tid]);
-                __syncthreads();
+        const int nch = (T + RS_CH - 1) / RS_CH;
+        for (int chi = 0; chi < nch; ++chi) {
+            const int ch = upper ? nch - 1 - chi : chi;
+            const int c0 = ch * RS_CH, cw = min(RS_CH, T - c0);
+            __syncthreads();  // v loaded / previous chunk consumed
+            // stage columns [c0, c0 + cw) of the block: rows are read 64 consecutive elements at a time
+            for (int e = tid; e < T * RS_CH; e += 128) {
+                const int r = e / RS_CH, cc = e % RS_CH;
+                if (cc < cw) s_blk[cc * LDB + r] = M[(k0 + r) * ld + k0 + c0 + cc];
             }
-        } else {
-            for (int q = T - 1; q >= 0; --q) {
-                if (tid == q) {
-                    cplx dg = M[(k0 + q) * ld + k0 + q];
-                    v[q] = (dg.x != 0.0 || dg.y != 0.0) ? cdiv(v[q], dg) : v[q];
+            __syncthreads();
+            if (upper) {
+                if (tid < cw) {
+                    const cplx dg = s_blk[tid * LDB + c0 + tid];
+                    rd[tid] = (dg.x != 0.0 || dg.y != 0.0) ? crecip(dg) : cmake(1.0, 0.0);
                 }
                 __syncthreads();
-                cplx xq = v[q];
-                if (tid < q) v[tid] = cfma(cmake(-M[(k0 + tid) * ld + k0 + q].x, -M[(k0 + tid) * ld + k0 + q].y), xq, v[tid]);
-                __syncthreads();
+                for (int q = c0 + cw - 1; q >= c0; --q) {
+                    if (tid == q) v[q] = cmul(v[q], rd[q - c0]);
+                    __syncthreads();
+                    const cplx xq = v[q], m = s_blk[(q - c0) * LDB + tid];
+                    if (tid < q) v[tid] = cfma(cmake(-m.x, -m.y), xq, v[tid]);
+                    __syncthreads();
+                }
+            } else {
+                for (int q = c0; q < c0 + cw; ++q) {
+                    const cplx xq = v[q], m = s_blk[(q - c0) * LDB + tid];
+                    if (tid > q && tid < T) v[tid] = cfma(cmake(-m.x, -m.y), xq, v[tid]);
+                    __syncthreads();
+                }
             }
         }
+        __syncthreads();
         if (tid < T) rhs[(k0 + tid) * nrhs + c] = v[tid];
         __syncthreads();
     }
 }
+static const size_t RS_SMEM = (size_t)RS_CH * (LU_NBO + 1) * sizeof(cplx);
 // permutation from sequential swaps, applied to a few columns (used by the stand-alone zgetrs)
 __global__ void rhs_apply_ipiv_kernel(const int32_t* __restrict__ ipiv, int64_t N, cplx* __restrict__ rhs, int nrhs) {
     if (blockIdx.x != 0) return;
@@ -674,6 +695,7 @@ static void lu_rec(LuCtx& x, int64_t j0, int w) {
 static int lu_factor(LuCtx& x) {
     cudaMemsetAsync(x.info, 0, sizeof(int32_t) * x.nbatch, x.st);
     cudaFuncSetAttribute(zgemm_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
+    cudaFuncSetAttribute(rhs_block_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM);
     // BHS_LU_GEMM_ONLY=1 (measurement aid, wrong results): issue only the trailing updates, to see how much of a
     // sweep's time the DMMA kernel accounts for on its own
     static const bool gemm_only = getenv("BHS_LU_GEMM_ONLY") != nullptr;
@@ -691,7 +713,7 @@ static int lu_factor(LuCtx& x) {
         if (x.rhs) {
             // forward substitution of this block row: y_J = L11^{-1} rhs_J ; rhs_below -= L21 y_J
             bhs_prof_begin(BHS_PROF_LU_RHS, x.st);
-            rhs_block_solve_kernel<<<dim3(1, 1, x.nbatch), 128, 0, x.st>>>(x.A, x.ld, J, w, 0, x.rhs, x.nrhs, x.bs.sA, x.bs.sRhs);
+            rhs_block_solve_kernel<<<dim3(1, 1, x.nbatch), 128, RS_SMEM, x.st>>>(x.A, x.ld, J, w, 0, x.rhs, x.nrhs, x.bs.sA, x.bs.sRhs);
             LU_LAUNCH_CHECK(x);
             if (J + w < x.N) {
                 rhs_gemv_sub_kernel<<<dim3((unsigned)cdiv64(x.N - J - w, 8), 1, x.nbatch), 256, 0, x.st>>>(
@@ -715,7 +737,7 @@ static int lu_backward(LuCtx& x) {
     for (int64_t bi = nblk - 1; bi >= 0; --bi) {
         int64_t J = bi * LU_NBO;
         int w = (int)((x.N - J < LU_NBO) ? (x.N - J) : LU_NBO);
-        rhs_block_solve_kernel<<<dim3(1, 1, x.nbatch), 128, 0, x.st>>>(x.A, x.ld, J, w, 1, x.rhs, x.nrhs, x.bs.sA, x.bs.sRhs);
+        rhs_block_solve_kernel<<<dim3(1, 1, x.nbatch), 128, RS_SMEM, x.st>>>(x.A, x.ld, J, w, 1, x.rhs, x.nrhs, x.bs.sA, x.bs.sRhs);
         LU_LAUNCH_CHECK(x);
         if (J > 0) {
             rhs_gemv_sub_kernel<<<dim3((unsigned)cdiv64(J, 8), 1, x.nbatch), 256, 0, x.st>>>(x.A, x.ld, 0, J, J, w, x.rhs, x.nrhs,
@@ -793,11 +815,12 @@ extern "C" int bhs_zgetrs(int64_t N, int nrhs, const double* d_LU, int64_t ld, c
     x.nbatch = 1;
     x.bs = LuBatch{0, 0, 0, 0, 0, 0, 0};
     x.st = (cudaStream_t)stream; x.err = 0;
+    cudaFuncSetAttribute(rhs_block_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM);
     rhs_apply_ipiv_kernel<<<1, 32, 0, x.st>>>(d_ipiv, N, x.rhs, nrhs);
     LU_LAUNCH_CHECK(x);
     for (int64_t J = 0; J < N; J += LU_NBO) {
         int w = (int)((N - J < LU_NBO) ? (N - J) : LU_NBO);
-        rhs_block_solve_kernel<<<1, 128, 0, x.st>>>(x.A, ld, J, w, 0, x.rhs, nrhs, 0, 0);
+        rhs_block_solve_kernel<<<1, 128, RS_SMEM, x.st>>>(x.A, ld, J, w, 0, x.rhs, nrhs, 0, 0);
         LU_LAUNCH_CHECK(x);
         if (J + w < N) {
             rhs_gemv_sub_kernel<<<(unsigned)cdiv64(N - J - w, 8), 256, 0, x.st>>>(x.A, ld, J + w, N, J, w, x.rhs, nrhs, 0, 0);
