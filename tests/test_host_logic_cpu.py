@@ -1,0 +1,74 @@
+"""Host-side logic that needs no GPU: synthetic geometries, the coordinate stand-in, the memory model, the input checks
+of the API mirror (they run before anything touches the device) and the no-CPU-fallback guarantee."""
+import numpy as np
+import pytest
+
+import biem_helmholtz_sphere_b200 as bhs
+from biem_helmholtz_sphere_b200 import _biem, geometry
+from oracle import biem_oracle as bo
+
+
+def test_grid_centers_match_reference_center_function():
+    # cli._center (cli.py:170-185) restated in the oracle; the package's copy must agree exactly
+    for half in (0, 1, 2, 4):
+        for d in (2, 3, 4):
+            assert np.array_equal(geometry.grid_centers(half, d), bo.grid_centers(half, d))
+    assert geometry.grid_centers(2, 3).shape == (16, 3)
+    ks = geometry.sweep_wavenumbers(256)
+    assert ks[0] == 0.5 and ks[-1] == 8.0 and len(ks) == 256
+    x = geometry.probe_ring(64, 10.0, 3)
+    assert x.shape == (3, 65) and np.allclose(np.linalg.norm(x[:, 1:], axis=0), 10.0) and not x[:, 0].any()
+    g = geometry.field_grid(8, 20.0, 3)
+    assert g.shape == (3, 8, 8) and g[0, 0, 0] == -20.0 and g[1, -1, -1] == 20.0 and not g[2].any()
+
+
+@pytest.mark.parametrize("bt", ["a", "ba", "bba"])
+def test_coordinate_stand_in_round_trip(bt):
+    c = bhs.create_from_branching_types(bt)
+    assert c.c_ndim == len(bt) + 1 and c.s_ndim == len(bt) and c.branching_types_expression_str == bt
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=(c.c_ndim, 50))
+    sph = c.from_cartesian(x)
+    back = c.to_cartesian(sph)
+    assert np.allclose(back, x, atol=1e-13)
+    o = bo.OracleCoordinates(bt).from_cartesian(x)
+    for k in sph:
+        assert np.allclose(sph[k], o[k])
+    with pytest.raises(NotImplementedError):
+        bhs.create_from_branching_types("caa")
+
+
+def test_memory_model_and_harmonic_counts():
+    # harm_n_ndim_le: 2-D 2n-1, 3-D n^2, 4-D n(n+1)(2n+1)/6   
+    for n in range(1, 12):
+        assert _biem.harm_n_ndim_le(n, c_ndim=2) == 2 * n - 1
+        assert _biem.harm_n_ndim_le(n, c_ndim=3) == n * n
+        assert _biem.harm_n_ndim_le(n, c_ndim=4) == n * (n + 1) * (2 * n + 1) // 6
+        assert _biem.harm_n_ndim_le(n, c_ndim=3) == bo.harm_count(3, n)
+    # max_memory / max_n_end keep the reference's model (_biem.py:23-74), including the element count for d <= 3
+    assert bhs.max_memory(c_ndim=3, n_end=16, n_balls=16) == 16 ** 2 * 256 ** 2
+    assert bhs.max_memory(c_ndim=4, n_end=3, n_balls=2) == 4 * (5 * 27) ** 2 * (11 * 6 ** 3) * 16
+    lim = bhs.max_memory(c_ndim=3, n_end=10, n_balls=4)
+    assert bhs.max_n_end(c_ndim=3, memory_limit=lim, n_balls=4) == 10
+
+
+def test_plane_wave_closures_and_shape_errors():
+    u, g = bhs.plane_wave(k=np.asarray(2.0), direction=np.array([3.0, 0.0, 4.0]))
+    x = np.array([[1.0, 0.0], [0.0, 1.0], [0.5, -0.5]])
+    assert np.allclose(u(x), np.exp(2j * (0.6 * x[0] + 0.8 * x[2])))
+    assert np.allclose(g(x), 2j * np.array([0.6, 0.0, 0.8])[:, None] * u(x)[None])
+    with pytest.raises(ValueError):
+        bhs.plane_wave(k=np.asarray(1.0), direction=np.ones((3, 2)))
+    with pytest.raises(ValueError):
+        bhs.point_source(k=np.asarray([1.0, 2.0]), source=np.zeros(3), n=0)
+
+
+def test_no_cpu_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    c = bhs.create_from_branching_types("ba")
+    with pytest.raises(Exception) as ei:
+        bhs.biem(c, k=np.asarray(1.0), n_end=3, centers=np.array([[0.0, 2.0, 0.0], [0.0, -2.0, 0.0]]), radii=np.ones(2))
+    assert "CUDA" in str(ei.value) or "cuda" in str(ei.value)
