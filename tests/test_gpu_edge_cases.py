@@ -181,3 +181,36 @@ def test_uscat_planar_fast_path_selection(bhs, case):
         nan = np.isnan(want)
         assert np.array_equal(nan, np.isnan(got))
         assert rel(got[~nan], want[~nan]) < 1e-11
+
+
+@pytest.mark.parametrize("alpha,beta", [(1.0, 0.0), (0.0, 1.0), (1.0, 0.5 + 0.2j)])
+def test_boundary_condition_residual_on_the_spheres(bhs, alpha, beta):
+    """Physics check that does not go through the oracle: the total field u_in + u_s of the GPU solution must
+    satisfy alpha u + beta du/dn = 0 on every sphere.  The normal derivative is a one-sided 4-point finite difference of
+    the GPU field, so the residual is limited by the difference formula (h^3), not by the solver."""
+    c = bhs.create_from_branching_types("ba")
+    cen = np.array([[0.0, 2.0, 0.0], [0.3, -2.1, 0.4], [3.6, 0.0, -0.5]])
+    rad = np.array([1.0, 0.8, 1.1])
+    k = np.asarray(1.3)
+    dirn = np.array([0.6, 0.0, 0.8])
+    uin, uin_grad = bhs.plane_wave(k=k, direction=dirn)
+    calc = bhs.biem(c, uin=uin, uin_grad=uin_grad, k=k, n_end=22, centers=cen, radii=rad, alpha=alpha, beta=beta,
+                    keep_matrix=False)
+    rng = np.random.default_rng(9)
+    y = rng.normal(size=(3, 40))
+    y /= np.linalg.norm(y, axis=0, keepdims=True)
+    h = 2e-3
+    worst = 0.0
+    for b in range(3):
+        f = []
+        for j in range(4):
+            x = cen[b][:, None] + rad[b] * (1.0 + 1e-9 + j * h) * y  # 1e-9: stay outside the NaN mask (r < rho) despite rounding
+            f.append(calc.uscat(x) + uin(x))
+        dn = (-11.0 * f[0] + 18.0 * f[1] - 9.0 * f[2] + 2.0 * f[3]) / (6.0 * h * rad[b])
+        res = alpha * f[0] + beta * dn
+        assert not np.any(np.isnan(res))
+        worst = max(worst, float(np.max(np.abs(res))))
+    print(f"\nboundary condition residual alpha={alpha} beta={beta}: {worst:.2e}")
+    # Dirichlet: floor = aliasing error of the reference's n_end-point RHS quadrature (4.7e-9 here); with beta != 0 the
+    # one-sided difference formula dominates (1.8e-7 / 1.7e-6 measured)
+    assert worst < (5e-8 if beta == 0.0 else 1e-5)
