@@ -1,0 +1,38 @@
+"""First-principles checks of the oracle that do not go through the scalar uscat(0) of the golden CSVs: the harmonics
+are orthonormal under the oracle's own quadrature, and the (S|R) translation matrix satisfies the addition theorem
+    S_{h'}(z + t) = sum_h (S|R)_{h',h}(t) R_h(z),   |z| < |t|          (_biem.py:522)
+point-wise.  These pin the matrix entries / index conventions that the golden values (basis-invariant scalars) cannot."""
+import numpy as np
+import pytest
+
+from oracle import biem_oracle as bo
+
+
+@pytest.mark.parametrize("btype,n_end", [("a", 9), ("ba", 7), ("bba", 5)])
+def test_harmonics_orthonormal(btype, n_end):
+    angles, w = bo.quadrature(btype, 2 * n_end)  # exact for products of two harmonics of degree < n_end
+    Y = bo.harmonics(btype, angles, n_end)  # [Q, H]
+    G = (Y.conj().T * w) @ Y
+    assert np.allclose(G, np.eye(G.shape[0]), atol=1e-12)
+
+
+@pytest.mark.parametrize("btype,n_end,k", [("a", 14, 1.3), ("ba", 12, 0.9), ("ba", 12, 2.0 + 0.5j), ("bba", 8, 1.1)])
+def test_translation_addition_theorem(btype, n_end, k):
+    d = len(btype) + 1
+    rng = np.random.default_rng(5)
+    coords = bo.OracleCoordinates(btype)
+    t = rng.normal(size=d)
+    t *= 4.0 / np.linalg.norm(t)
+    T = bo.translation_coef(btype, t[:, None], k, n_end)[0]  # [H', H]
+    deg = bo.degree_table(btype, n_end)
+    nlow = 4  # singular functions S_{h'} of low degree: the series in h converges like (|z| / |t|)^n
+    for _ in range(5):
+        z = rng.normal(size=d)
+        z *= (0.35 if d < 4 else 0.1) / np.linalg.norm(z)  # truncation error ~ (|z| / |t|)^n_end: 4-D runs a shorter series
+        sz = coords.from_cartesian((z + t)[:, None])
+        S = (bo.radial(d, n_end - 1, k * sz["r"], "h")[deg, 0] * bo.harmonics(btype, [sz[i] for i in range(d - 1)], n_end)[0])
+        rz = coords.from_cartesian(z[:, None])
+        R = (bo.radial(d, n_end - 1, k * rz["r"], "j")[deg, 0] * bo.harmonics(btype, [rz[i] for i in range(d - 1)], n_end)[0])
+        lhs = S[deg < nlow]
+        rhs = (T @ R)[deg < nlow]
+        assert np.max(np.abs(lhs - rhs)) < 1e-9 * np.max(np.abs(lhs)), (btype, np.max(np.abs(lhs - rhs)))
