@@ -2,7 +2,7 @@
 
 The hot path only touches ``c.c_ndim``, ``c.s_ndim``, ``c.root``, ``c.from_cartesian``, ``c.to_cartesian``
 and ``c.branching_types_expression_str`` (reference: _biem.py:321,593,613,617,652,699,885; plot.py:106).
-Supported trees are the chains ``'a'`` (2-D), ``'ba'`` (3-D), ``'bba'`` (4-D): convention decoded from the
+Supported trees are the chains ``'a'`` (2-D), ``'ba'`` (3-D), ``'bba'`` (4-D), ... ``'bbbbbba'`` (8-D): convention decoded from the
 reference's a.svg / ba.svg / bba.svg,
 
     x0 = r cos t0,  x1 = r sin t0 cos t1, ...,  x_{d-1} = r sin t0 ... sin t_{d-2}.
@@ -15,7 +15,7 @@ from __future__ import annotations
 
 import numpy as np
 
-SUPPORTED = ("a", "ba", "bba")
+SUPPORTED = ("a", "ba", "bba", "bbba", "bbbba", "bbbbba", "bbbbbba")  # chains up to d = 8
 
 
 class SphericalCoordinates:

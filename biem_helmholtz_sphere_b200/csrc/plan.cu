@@ -238,7 +238,7 @@ static int build_coupling(bhs_plan* p) {
     std::vector<std::vector<Term>> terms((size_t)H * H);
     // rows h are independent: split them over host threads (the triple integrals are long-double quadratures,
     // 2.5e9 multiply-adds at n_end = 39)
-    if (d != 3 && d != 4) return BHS_ERR_UNSUPPORTED;
+    if (d < 3) return BHS_ERR_UNSUPPORTED;
     const std::map<std::vector<int>, int>& lk2 = lookup2;  // read-only from here on
     auto row_work = [&](int h, int64_t& cnt) {
         if (d == 3) {
@@ -252,6 +252,53 @@ static int build_coupling(bhs_plan* p) {
                     ld g = triple(0, np, std::abs(mp), n, std::abs(m), n2, std::abs(m2)) * inv_s2pi;
                     tv.push_back({lk2.at({n2, m2}), (double)(cd * g)});
                     ++cnt;
+                }
+            }
+        } else if (d >= 5) {
+            // chains of any depth: one Gegenbauer triple integral per b-node (node i has d-2-i descendants); the lower
+            // indices of node i are the degrees chosen at node i+1 (|m| at the innermost b-node).  Enumerated from the
+            // azimuth outwards with an explicit stack of (n''_i) choices.
+            const int nb = s - 1;  // number of b-nodes
+            const int32_t* ih = tab + (size_t)h * s;
+            for (int hp = 0; hp < H; ++hp) {
+                const int32_t* ip = tab + (size_t)hp * s;
+                const int m2 = ip[s - 1] - ih[s - 1];
+                std::vector<Term>& tv = terms[(size_t)h * H + hp];
+                int n2[BHS_MAX_NODES + 1];
+                ld gacc[BHS_MAX_NODES + 2];
+                // depth-first over nodes i = nb-1 .. 0
+                int i = nb - 1;
+                gacc[nb] = 1.0L;
+                n2[nb] = std::abs(m2);  // lower index of the innermost node
+                int cur[BHS_MAX_NODES + 1];
+                auto first = [&](int node) {
+                    int lo = std::abs(ih[node] - ip[node]);
+                    int low2 = n2[node + 1];
+                    while (lo < low2) lo += 2;
+                    return lo;
+                };
+                cur[i] = first(i);
+                while (i < nb) {
+                    if (cur[i] > ih[i] + ip[i]) {  // exhausted: back up
+                        ++i;
+                        if (i < nb) cur[i] += 2;
+                        continue;
+                    }
+                    const int lowp = (i + 1 < nb) ? ip[i + 1] : std::abs(ip[s - 1]);
+                    const int lowh = (i + 1 < nb) ? ih[i + 1] : std::abs(ih[s - 1]);
+                    n2[i] = cur[i];
+                    gacc[i] = gacc[i + 1] * triple(i, ip[i], lowp, ih[i], lowh, n2[i], n2[i + 1]);
+                    if (i == 0) {
+                        std::vector<int> key(s);
+                        for (int q = 0; q < nb; ++q) key[q] = n2[q];
+                        key[s - 1] = m2;
+                        tv.push_back({lk2.at(key), (double)(cd * gacc[0] * inv_s2pi)});
+                        ++cnt;
+                        cur[0] += 2;
+                    } else {
+                        --i;
+                        cur[i] = first(i);
+                    }
                 }
             }
         } else {
@@ -344,7 +391,7 @@ extern "C" int bhs_plan_create(int d, int n_end, bhs_plan_t** out) {
     if (!out) return BHS_ERR_INVALID;
     *out = nullptr;
     if (d < 2 || n_end < 1) return BHS_ERR_INVALID;
-    if (d > 4) return BHS_ERR_UNSUPPORTED;  // coupling tables: chain types a, ba, bba
+    if (d - 2 > BHS_MAX_NODES) return BHS_ERR_UNSUPPORTED;  // chain types a, ba, bba, bbba, ... up to d = 8
     bhs_plan* p = new (std::nothrow) bhs_plan();
     if (!p) return BHS_ERR_ALLOC;
     p->d = d;

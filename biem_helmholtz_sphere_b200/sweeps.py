@@ -4,7 +4,7 @@ Restates the two batch commands of the reference CLI that produced its golden da
 and ``accuracy`` (cli.py:188-271) -- minus the typer/tqdm/matplotlib front-end: same loops, same geometries
 (``_center``, cli.py:170-185), same call into ``biem`` (plane wave built with k = 1 whatever the solve wavenumber,
 cli.py:239 vs :244), same NaN checks, same CSV columns, so that the output can be diffed row by row against
-``accuracy/*.csv`` / ``jascome/jascome_output.csv``.  Only the chain trees a / ba / bba are available here.
+``accuracy/*.csv`` / ``jascome/jascome_output.csv``.  Only the chain trees a / ba / bba / bbba / ... are available here.
 
     python -m biem_helmholtz_sphere_b200.sweeps jascome  [--out jascome_output.csv] [--branching-types a,ba,bba]
     python -m biem_helmholtz_sphere_b200.sweeps accuracy [--out accuracy.csv] [--branching-types a] [--max-n-end 512]

@@ -13,7 +13,7 @@
  *     synchronising; calls are re-entrant, there is no hidden global state except the plan cache
  *     objects the caller owns;
  *   - return value: 0 = ok, <0 = invalid argument (BHS_ERR_*), >0 = cudaError_t of a failed launch;
- *   - coordinate types are the chain trees 'a' (d=2), 'ba' (d=3), 'bba' (d=4): passed as `d`;
+ *   - coordinate types are the chain trees 'a' (d=2), 'ba' (d=3), 'bba' (d=4), 'bbba' (d=5), ... up to d=8: passed as `d`;
  *   - wavenumbers are real arrays `d_k`; an optional `d_k_im` (NULL = real wavenumbers) adds imaginary parts
  *     (absorbing media, Im k != 0); h_n^{(1)} is then always computed directly (never as j + i y, which cancels);
  *   - matrices are ROW-major (C order), exactly the reference's [..., B, harm, B', harm'] layout.

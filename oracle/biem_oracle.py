@@ -314,7 +314,30 @@ def coupling_matrix(btype: str, n_end: int):
                         cols.append(lookup2[(n2, l2, m2)])
                         vals.append(cd * _ipow(np.asarray(n_ + n2 - n_p)) * g)
     else:
-        raise NotImplementedError("oracle coupling implemented for d = 2, 3, 4")
+        # chains of any depth (d >= 5): product of one Gegenbauer triple integral per b-node; the lower indices of node i
+        # are the degrees of node i + 1 (|m| for the innermost b-node).  Enumerated from the azimuth outwards.
+        for hp in range(H):
+            ip = tab[hp]
+            for h in range(H):
+                ih = tab[h]
+                m2 = int(ip[s - 1] - ih[s - 1])
+
+                def rec(i, low_p, low_h, low_2, tail, g):
+                    # node i (desc = s - 1 - i), lower indices known; choose n''_i
+                    n_p, n_ = int(ip[i]), int(ih[i])
+                    I = triple(s - 1 - i, low_p, low_h, low_2)
+                    for n2 in range(abs(n_p - n_), n_p + n_ + 1, 2):
+                        if n2 < low_2:
+                            continue
+                        gg = g * I[n_p, n_, n2]
+                        if i == 0:
+                            rows.append(hp * H + h)
+                            cols.append(lookup2[(n2,) + tail])
+                            vals.append(cd * _ipow(np.asarray(n_ + n2 - n_p)) * gg * inv_s2pi)
+                        else:
+                            rec(i - 1, n_p, n_, n2, (n2,) + tail, gg)
+
+                rec(s - 2, abs(int(ip[s - 1])), abs(int(ih[s - 1])), abs(m2), (m2,), 1.0)
     M = scipy.sparse.csr_matrix(
         (np.asarray(vals, dtype=np.complex128), (np.asarray(rows), np.asarray(cols))), shape=(H * H, H2)
     )

@@ -8,7 +8,7 @@ import pytest
 from oracle import biem_oracle as bo
 
 
-@pytest.mark.parametrize("btype,n_end", [("a", 9), ("ba", 7), ("bba", 5)])
+@pytest.mark.parametrize("btype,n_end", [("a", 9), ("ba", 7), ("bba", 5), ("bbba", 4), ("bbbba", 3)])
 def test_harmonics_orthonormal(btype, n_end):
     angles, w = bo.quadrature(btype, 2 * n_end)  # exact for products of two harmonics of degree < n_end
     Y = bo.harmonics(btype, angles, n_end)  # [Q, H]
@@ -16,7 +16,8 @@ def test_harmonics_orthonormal(btype, n_end):
     assert np.allclose(G, np.eye(G.shape[0]), atol=1e-12)
 
 
-@pytest.mark.parametrize("btype,n_end,k", [("a", 14, 1.3), ("ba", 12, 0.9), ("ba", 12, 2.0 + 0.5j), ("bba", 8, 1.1)])
+@pytest.mark.parametrize("btype,n_end,k", [("a", 14, 1.3), ("ba", 12, 0.9), ("ba", 12, 2.0 + 0.5j), ("bba", 8, 1.1),
+                                           ("bbba", 6, 1.2), ("bbbba", 5, 0.8)])
 def test_translation_addition_theorem(btype, n_end, k):
     d = len(btype) + 1
     rng = np.random.default_rng(5)
@@ -25,10 +26,10 @@ def test_translation_addition_theorem(btype, n_end, k):
     t *= 4.0 / np.linalg.norm(t)
     T = bo.translation_coef(btype, t[:, None], k, n_end)[0]  # [H', H]
     deg = bo.degree_table(btype, n_end)
-    nlow = 4  # singular functions S_{h'} of low degree: the series in h converges like (|z| / |t|)^n
+    nlow = 4 if d < 5 else 2  # singular functions S_{h'} of low degree: the series in h converges like (|z| / |t|)^n
     for _ in range(5):
         z = rng.normal(size=d)
-        z *= (0.35 if d < 4 else 0.1) / np.linalg.norm(z)  # truncation error ~ (|z| / |t|)^n_end: 4-D runs a shorter series
+        z *= (0.35 if d < 4 else 0.1 if d == 4 else 0.03) / np.linalg.norm(z)  # truncation ~ (|z| / |t|)^n_end: shorter series in high d
         sz = coords.from_cartesian((z + t)[:, None])
         S = (bo.radial(d, n_end - 1, k * sz["r"], "h")[deg, 0] * bo.harmonics(btype, [sz[i] for i in range(d - 1)], n_end)[0])
         rz = coords.from_cartesian(z[:, None])
