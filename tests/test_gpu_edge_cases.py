@@ -152,8 +152,9 @@ def test_hand_built_result_record(bhs):
     assert rel(rec.uscat(x, per_ball=True)[ok], ref.uscat(x, per_ball=True)[ok]) < TOL
 
 
+@pytest.mark.parametrize("k", [2.3, 1.1 + 0.7j])
 @pytest.mark.parametrize("case", ["coplanar", "points_off_plane", "centres_off_plane", "negative_side"])
-def test_uscat_planar_fast_path_selection(bhs, case):
+def test_uscat_planar_fast_path_selection(bhs, case, k):
     """The 3-D field kernel has a device-selected fast path for points and centres that all share one x2 (planar heat
     maps).  Both selections must agree with the oracle, including points on both sides of a ball (azimuth 0 and pi)."""
     from biem_helmholtz_sphere_b200 import _ops
@@ -173,11 +174,11 @@ def test_uscat_planar_fast_path_selection(bhs, case):
     if case == "negative_side":
         x[1] = -np.abs(x[1]) - 3.5  # every point has dx1 < 0 for every ball
     x[:, 0] = [0.0, 2.0 + 2.0, 0.4]  # on the in-plane axis through ball 0's centre
-    res = bo.OracleResult(c=bo.OracleCoordinates("ba"), centers=cen.T.copy(), radii=rad, k=2.3, n_end=n_end, eta=0.8,
+    res = bo.OracleResult(c=bo.OracleCoordinates("ba"), centers=cen.T.copy(), radii=rad, k=k, n_end=n_end, eta=0.8,
                           kind="outer", density=dens, matrix=None)
     for pb in (False, True):
         want = bo.biem_u(res, x, per_ball=pb)
-        got = _ops.uscat(3, n_end, cen, rad, 2.3, 0.8, dens, x, per_ball=pb).cpu().numpy()
+        got = _ops.uscat(3, n_end, cen, rad, k, 0.8, dens, x, per_ball=pb).cpu().numpy()
         nan = np.isnan(want)
         assert np.array_equal(nan, np.isnan(got))
         assert rel(got[~nan], want[~nan]) < 1e-11
