@@ -1,7 +1,7 @@
 """Replay of the reference's golden CSVs through the public API (tools/golden_sweep.py): every 2-D row up to the
 reference's largest published run (n_end = 3444, N = 13 774, k up to 4096), every grid row (up to 256 discs), every
-forced-`triplet` row of the supported trees, and every 4th 3-D row (all 390 are run by the tool itself; the complete
-result of the last full run is committed as profiles/r01_golden_sweep.json).  Tolerance 1e-10 relative."""
+forced-`triplet` row of the supported trees, and all 390 3-D rows (n_end <= 39) -- 1243 rows in total; the result of the
+last full run is also committed as profiles/r01_golden_sweep.json.  Tolerance 1e-10 relative."""
 import os
 import sys
 
@@ -21,9 +21,9 @@ def test_golden_csv_replay():
         r = res2[name]
         assert r["run"] == r["rows"] and r["skipped"] == 0, (name, r)
         assert r["outside_tolerance"] == 0, (name, r)
-    res3 = gs.sweep(stride=4, max_n_end_2d=0, max_n_end_3d=39)
+    res3 = gs.sweep(stride=1, max_n_end_2d=0, max_n_end_3d=39)
     r = res3["accuracy_k_ba.csv[ba]"]
-    assert r["run"] >= 97 and r["outside_tolerance"] == 0, r
+    assert r["run"] == r["rows"] == 390 and r["outside_tolerance"] == 0, r
     full = gs.sweep(stride=1, max_n_end_2d=64, max_n_end_3d=16)["jascome_output.csv"]
     assert full["run"] == full["rows"] == 24 and full["outside_tolerance"] == 0, full
 
