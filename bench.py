@@ -391,7 +391,13 @@ def run_b200(args) -> None:
         del wbuf
         if am["ms"] > 0:
             gbs = am["work"] / (am["ms"] * 1e-3) * 1e-9
+            nterms, _ = _ops.get_plan(3, N_END).coupling_stats()
+            counted = (B * B - B) * (8.0 * nterms + 12.0 * H * H)  # 8 flop per coupling term + 12 per entry, per pair
+            ctf = counted / (am["ms"] / nprof * 1e-3) * 1e-12
             out["assembly"] = {"gbs": gbs, "ms": am["ms"] / nprof, "hbm_peak_gbs": hbm, "frac_hbm": gbs / hbm,
+                               "counted_tflops": ctf, "frac_fp64_counted": ctf / peak_dfma,
+                               "counted_note": "SURVEY 8d flop count per ordered pair; the kernel executes it once per DISTINCT "
+                                               "translation vector (48 of 240 pairs on this grid)",
                                "write_stream_gbs": wbest, "frac_write_stream": gbs / wbest,
                                "note": "hbm_peak_gbs is MEASURED_PEAKS.json's copy figure (read + write bytes); "
                                        "write_stream_gbs is a 4 GiB fill measured in this run"}
