@@ -90,8 +90,11 @@ def rhs_expand(d: int, n_end: int, *, g=None, centers=None, radii=None, k_in=Non
 
 
 def assemble(d: int, n_end: int, centers, radii, k, eta=None, alpha=None, beta=None, out=None, work=None,
-             k_im=None) -> torch.Tensor:
-    """A [nsys, N, N] row-major   (bhs_assemble); wavenumbers k + i k_im (k_im None = real)."""
+             k_im=None, rows: tuple[int, int] | None = None) -> torch.Tensor:
+    """A [nsys, N, N] row-major   (bhs_assemble); wavenumbers k + i k_im (k_im None = real).
+
+    ``rows=(b_lo, b_hi)``: only the block rows of the row balls b_lo <= b < b_hi, as a strip [nsys, (b_hi-b_lo) H, N]
+    (bhs_assemble_rows: the unit of the multi-GPU block-row sharding)."""
     plan = get_plan(d, n_end)
     cen, rad, kk = _f64(centers), _f64(radii), _f64(k).reshape(-1)
     B = rad.shape[0]
@@ -100,13 +103,20 @@ def assemble(d: int, n_end: int, centers, radii, k, eta=None, alpha=None, beta=N
     et = None if eta is None else _f64(eta).reshape(-1)
     al = None if alpha is None else _c128(alpha)
     be = None if beta is None else _c128(beta)
+    b_lo, b_hi = (0, B) if rows is None else rows
+    nrow = (b_hi - b_lo) * plan.H
     if out is None:
-        out = torch.empty((nsys, N, N), dtype=C128, device=cen.device)
+        out = torch.empty((nsys, nrow, N), dtype=C128, device=cen.device)
     if work is None:
         work = _work(load().bhs_assemble_workspace(plan.handle, B, nsys))
     kim = None if k_im is None else _f64(k_im).reshape(-1)
-    check(load().bhs_assemble(plan.handle, B, nsys, ptr(cen), ptr(rad), ptr(kk), ptr(kim), ptr(et), ptr(al), ptr(be),
-                              ptr(out), N, N * N, ptr(work), stream_ptr()), "bhs_assemble")
+    if rows is None:
+        check(load().bhs_assemble(plan.handle, B, nsys, ptr(cen), ptr(rad), ptr(kk), ptr(kim), ptr(et), ptr(al), ptr(be),
+                                  ptr(out), N, N * N, ptr(work), stream_ptr()), "bhs_assemble")
+    else:
+        check(load().bhs_assemble_rows(plan.handle, B, nsys, ptr(cen), ptr(rad), ptr(kk), ptr(kim), ptr(et), ptr(al),
+                                       ptr(be), b_lo, b_hi, ptr(out), N, nrow * N, ptr(work), stream_ptr()),
+              "bhs_assemble_rows")
     return out
 
 

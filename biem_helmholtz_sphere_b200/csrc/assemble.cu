@@ -141,15 +141,15 @@ __global__ void __launch_bounds__(1024) pair_group_kernel(int B, const int32_t* 
 }
 
 // diagonal blocks A[(b,h),(b,h')] = delta_{hh'} diag[s][b][h]
-__global__ void diag_blocks_kernel(int B, int H, const cplx* __restrict__ diag, cplx* __restrict__ A, int64_t ld,
+__global__ void diag_blocks_kernel(int B, int H, int b_lo, const cplx* __restrict__ diag, cplx* __restrict__ A, int64_t ld,
                                    int64_t sys_stride) {
-    const int sys = blockIdx.z, b = blockIdx.y;
+    const int sys = blockIdx.z, b = b_lo + blockIdx.y;
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= (int64_t)H * H) return;
     const int h = (int)(e / H), hp = (int)(e % H);
     cplx v = cmake(0.0, 0.0);
     if (h == hp) v = diag[((int64_t)sys * B + b) * H + h];
-    A[(int64_t)sys * sys_stride + ((int64_t)b * H + h) * ld + (int64_t)b * H + hp] = v;
+    A[(int64_t)sys * sys_stride + ((int64_t)(b - b_lo) * H + h) * ld + (int64_t)b * H + hp] = v;
 }
 
 struct SmArrA {
@@ -265,6 +265,7 @@ __global__ void factors_z_kernel(int d, int L, int H, int B, int nsys, const dou
 // ---- the assembly kernel --------------------------------------------------------------------------------
 struct AsmArgs {
     int B, H, H2, L2, nt_res;
+    int b_lo, b_hi;            // block rows (row balls) written by this call; the strip starts at row ball b_lo
     int sy_global;             // 1: the S window does not fit in shared memory, gather from global (huge 2-D bands)
     const int32_t* n_unique;   // [1]   number of distinct translation vectors U
     const int32_t* grp_rep;    // [U]   representative pair of each
@@ -378,6 +379,7 @@ __global__ void __launch_bounds__(ASM_THREADS) assemble_kernel(AsmArgs a) {
                 const int pk = (q0 + i < q_end) ? __ldg(a.members + q0 + i) : -1;
                 bb[i] = pk >> 16;
                 bq[i] = pk & 0xffff;
+                if (bb[i] < a.b_lo || bb[i] >= a.b_hi) bb[i] = -1;  // row ball outside the strip of this call
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -395,7 +397,7 @@ __global__ void __launch_bounds__(ASM_THREADS) assemble_kernel(AsmArgs a) {
 #pragma unroll
                 for (int q = 0; q < ASM_EPT; ++q)
                     if (ok_[q])
-                        Asys[((int64_t)bb[i] * a.H + h_[q]) * a.ld + (int64_t)bq[i] * a.H + hp_[q]] =
+                        Asys[((int64_t)(bb[i] - a.b_lo) * a.H + h_[q]) * a.ld + (int64_t)bq[i] * a.H + hp_[q]] =
                             cmul(cmul(cmake(ar[q], ai[q]), rf[i][q]), cf[i][q]);
             }
         }
@@ -474,11 +476,12 @@ static int run_factors(const bhs_plan* p, int B, int nsys, const double* d_radii
 
 int bhs_launch_harmonics_band2(const bhs_plan* plan, const double* d_xyz, int64_t npts, cplx* d_out, cudaStream_t st);
 
-extern "C" int bhs_assemble(const bhs_plan_t* plan, int B, int nsys, const double* d_centers, const double* d_radii,
-                            const double* d_k, const double* d_k_im, const double* d_eta, const double* d_alpha,
-                            const double* d_beta, double* d_A, int64_t ld, int64_t sys_stride, void* d_work,
-                            void* stream) {
+static int assemble_impl(const bhs_plan_t* plan, int B, int nsys, const double* d_centers, const double* d_radii,
+                         const double* d_k, const double* d_k_im, const double* d_eta, const double* d_alpha,
+                         const double* d_beta, int b_lo, int b_hi, double* d_A, int64_t ld, int64_t sys_stride, void* d_work,
+                         void* stream) {
     if (!plan || B <= 0 || nsys <= 0 || !d_centers || !d_radii || !d_k || !d_A || !d_work) return BHS_ERR_INVALID;
+    if (b_lo < 0 || b_hi > B || b_lo >= b_hi) return BHS_ERR_INVALID;
     const int64_t N = (int64_t)B * plan->H;
     if (ld < N) return BHS_ERR_INVALID;
     if (B > 32767) return BHS_ERR_UNSUPPORTED;  // pairs are packed as (b << 16) | b' in 32 bits
@@ -537,6 +540,7 @@ extern "C" int bhs_assemble(const bhs_plan_t* plan, int B, int nsys, const doubl
     BHS_CHECK_LAUNCH();
     AsmArgs a;
     a.B = B; a.H = plan->H; a.H2 = plan->H2; a.L2 = plan->L2;
+    a.b_lo = b_lo; a.b_hi = b_hi;
     a.n_unique = w.n_unique; a.grp_rep = w.grp_rep; a.grp_start = w.grp_start; a.members = w.members;
     a.tiles = plan->d_tiles; a.coef = plan->d_coef; a.cidx = plan->d_cidx; a.deg2 = plan->d_deg2;
     a.Y2 = w.Y2; a.hp = w.hp; a.rowf = w.rowf; a.colf = w.colf; a.diag = w.diag;
@@ -565,16 +569,35 @@ extern "C" int bhs_assemble(const bhs_plan_t* plan, int B, int nsys, const doubl
     bhs_prof_begin(BHS_PROF_ASM_MAIN, st);
     {
         const int64_t hh = (int64_t)plan->H * plan->H;
-        dim3 dgrid((unsigned)((hh + 255) / 256), (unsigned)B, (unsigned)nsys);
-        diag_blocks_kernel<<<dgrid, 256, 0, st>>>(B, plan->H, w.diag, (cplx*)d_A, ld, sys_stride);
+        dim3 dgrid((unsigned)((hh + 255) / 256), (unsigned)(b_hi - b_lo), (unsigned)nsys);
+        diag_blocks_kernel<<<dgrid, 256, 0, st>>>(B, plan->H, b_lo, w.diag, (cplx*)d_A, ld, sys_stride);
         BHS_CHECK_LAUNCH();
     }
     if (B > 1) {
         assemble_kernel<<<grid, ASM_THREADS, smem, st>>>(a);
         BHS_CHECK_LAUNCH();
     }
-    bhs_prof_end(BHS_PROF_ASM_MAIN, 16.0 * (double)N * (double)N * nsys, st);
+    bhs_prof_end(BHS_PROF_ASM_MAIN, 16.0 * (double)(b_hi - b_lo) * plan->H * (double)N * nsys, st);
     return BHS_OK;
+}
+
+extern "C" int bhs_assemble(const bhs_plan_t* plan, int B, int nsys, const double* d_centers, const double* d_radii,
+                            const double* d_k, const double* d_k_im, const double* d_eta, const double* d_alpha,
+                            const double* d_beta, double* d_A, int64_t ld, int64_t sys_stride, void* d_work,
+                            void* stream) {
+    return assemble_impl(plan, B, nsys, d_centers, d_radii, d_k, d_k_im, d_eta, d_alpha, d_beta, 0, B, d_A, ld, sys_stride,
+                         d_work, stream);
+}
+
+// Block rows b in [b_lo, b_hi) only, written to a strip [(b_hi - b_lo) * H, ld] whose first row is (b_lo, h = 0): the
+// unit of the multi-GPU "assembly block-row" sharding (each rank builds its strip, strips are all-gathered onto the
+// rank that factorises).  Same workspace as bhs_assemble.
+extern "C" int bhs_assemble_rows(const bhs_plan_t* plan, int B, int nsys, const double* d_centers, const double* d_radii,
+                                 const double* d_k, const double* d_k_im, const double* d_eta, const double* d_alpha,
+                                 const double* d_beta, int b_lo, int b_hi, double* d_A, int64_t ld, int64_t sys_stride,
+                                 void* d_work, void* stream) {
+    return assemble_impl(plan, B, nsys, d_centers, d_radii, d_k, d_k_im, d_eta, d_alpha, d_beta, b_lo, b_hi, d_A, ld,
+                         sys_stride, d_work, stream);
 }
 
 extern "C" int bhs_diag_coef(const bhs_plan_t* plan, int B, int nsys, const double* d_radii, const double* d_k,

@@ -6,6 +6,8 @@ The path shards three natural ways and none of them has an exchange step (SURVEY
   outputs (density 64 KB per k at C3, probe values) are all-gathered afterwards only if the caller wants them everywhere;
 * field evaluation    -- contiguous row tiles of the point grid per rank, after ONE broadcast of the solved density
   (590 KB at C5) from the rank that solved the system: the only collective on the data path;
+* assembly of ONE large system -- block rows (all harmonics of a row ball) per rank, then an all-gather of the strips
+  onto every rank (21.7 GB at C5, ~25 ms over NVLink): optional, the single-GPU assembly is already 0.2 % of the solve;
 * the LU of one system does not shard (replicas only).
 
 Everything here is host logic over tensors that live wherever the process group's backend wants them (CUDA for NCCL, CPU
@@ -204,3 +206,59 @@ def uscat_sharded(c: Any, *, centers, radii, k: float, eta: float, n_end: int, d
     if not gather or world == 1:
         return u
     return all_gather_rows(u, n0, group)
+
+
+def ball_rows(B: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous range of row balls [b_lo, b_hi) assembled by ``rank`` (sizes differ by at most one ball)."""
+    sl = field_rows(B, rank, world)
+    return sl.start, sl.stop
+
+
+def _default_assemble_rows(c, centers, radii, k, eta, n_end, alpha, beta, b_lo, b_hi):
+    from . import _ops
+    from ._coords import branching_types_of
+
+    d = len(branching_types_of(c)) + 1
+    dev = torch.device("cuda", torch.cuda.current_device())
+    kc = complex(k)
+    kk = torch.tensor([kc.real], dtype=torch.float64, device=dev)
+    kim = torch.tensor([kc.imag], dtype=torch.float64, device=dev) if kc.imag != 0.0 else None
+    et = torch.tensor([float(eta)], dtype=torch.float64, device=dev)
+    B = np.asarray(radii).shape[0]
+    al = torch.as_tensor(np.broadcast_to(np.asarray(alpha, dtype=np.complex128), (B,)).copy(), device=dev)
+    be = torch.as_tensor(np.broadcast_to(np.asarray(beta, dtype=np.complex128), (B,)).copy(), device=dev)
+    return _ops.assemble(d, n_end, torch.as_tensor(np.asarray(centers), device=dev),
+                         torch.as_tensor(np.asarray(radii), device=dev), kk, et, al, be, k_im=kim, rows=(b_lo, b_hi))[0]
+
+
+def assemble_sharded(c: Any, *, centers, radii, k, eta: float, n_end: int, alpha=1.0, beta=0.0, gather: bool = True,
+                     group=None, assemble_rows: Callable | None = None) -> torch.Tensor:
+    """System matrix of ONE wavenumber with the block rows split over the ranks (rank r builds the rows of the row balls
+    :func:`ball_rows`), then -- if ``gather`` -- an all-gather of the strips so that every rank holds the full
+    ``[N, N]`` matrix.  Returns this rank's strip ``[(b_hi - b_lo) H, N]`` otherwise."""
+    rank, world = dist_info(group)
+    B = np.asarray(radii).shape[0]
+    b_lo, b_hi = ball_rows(B, rank, world)
+    fn = assemble_rows or _default_assemble_rows
+    if b_hi > b_lo:
+        strip = torch.as_tensor(fn(c, centers, radii, k, eta, n_end, alpha, beta, b_lo, b_hi))
+    else:
+        strip = None
+    if not gather or world == 1:
+        return strip
+    meta = [None] * world
+    dist.all_gather_object(meta, None if strip is None else (int(strip.shape[0] // (b_hi - b_lo)), int(strip.shape[1])), group=group)
+    H, N = next(m for m in meta if m is not None)
+    dev = _comm_device(group)
+    bmax = -(-B // world)
+    buf = torch.zeros((bmax * H, N), dtype=torch.complex128, device=dev)
+    if strip is not None:
+        buf[: strip.shape[0]] = strip.to(dev)
+    parts = [torch.empty_like(torch.view_as_real(buf)) for _ in range(world)]
+    dist.all_gather(parts, torch.view_as_real(buf).contiguous(), group=group)
+    out = []
+    for r in range(world):
+        lo, hi = ball_rows(B, r, world)
+        out.append(torch.view_as_complex(parts[r])[: (hi - lo) * H])
+    full = torch.cat(out, dim=0)
+    return full if strip is None else full.to(strip.device)

@@ -110,6 +110,13 @@ int bhs_assemble(const bhs_plan_t *plan, int B, int nsys, const double *d_center
                  const double *d_alpha, const double *d_beta, double *d_A, int64_t ld,
                  int64_t sys_stride, void *d_work, void *stream);
 
+/* Block rows b in [b_lo, b_hi) only, into a strip [(b_hi - b_lo) * H, ld] per system whose first row is (b_lo, h = 0):
+ * the unit of the multi-GPU assembly block-row sharding.  Same workspace as bhs_assemble. */
+int bhs_assemble_rows(const bhs_plan_t *plan, int B, int nsys, const double *d_centers,
+                      const double *d_radii, const double *d_k, const double *d_k_im,
+                      const double *d_eta, const double *d_alpha, const double *d_beta, int b_lo, int b_hi,
+                      double *d_A, int64_t ld, int64_t sys_stride, void *d_work, void *stream);
+
 /* single-sphere shortcut diag[s, b, h] = SD_n (alpha h_n + beta k h_n')  (_biem.py:648-691) */
 int bhs_diag_coef(const bhs_plan_t *plan, int B, int nsys, const double *d_radii, const double *d_k,
                   const double *d_k_im, const double *d_eta, const double *d_alpha, const double *d_beta,

@@ -160,6 +160,27 @@ def test_assemble(ops, d, n_end, B):
         assert e_abs < 1e-12
 
 
+@pytest.mark.parametrize("d,n_end,B", [(2, 9, 5), (3, 7, 4), (4, 4, 3)])
+def test_assemble_rows_strips(ops, d, n_end, B):
+    """bhs_assemble_rows: the strips of any split of the row balls are bit-identical to the rows of the full matrix."""
+    import torch
+
+    rng = np.random.default_rng(d)
+    centers = np.zeros((B, d))
+    centers[:, 1] = 4.0 * np.arange(B) - 2.0 * (B - 1)
+    centers[:, 0] = rng.uniform(-0.3, 0.3, size=B)
+    radii = rng.uniform(0.7, 1.1, size=B)
+    k, eta = np.array([1.3]), np.array([0.8])
+    al = rng.normal(size=B) + 1j * rng.normal(size=B)
+    be = rng.normal(size=B) + 1j * rng.normal(size=B)
+    full = ops.assemble(d, n_end, centers, radii, k, eta, al, be)[0]
+    H = full.shape[0] // B
+    for b_lo, b_hi in ((0, 1), (1, B), (B - 1, B), (0, B), (1, 2)):
+        strip = ops.assemble(d, n_end, centers, radii, k, eta, al, be, rows=(b_lo, b_hi))[0]
+        assert strip.shape == ((b_hi - b_lo) * H, B * H)
+        assert torch.equal(strip, full[b_lo * H : b_hi * H])
+
+
 @pytest.mark.parametrize("M,N,K", [(64, 64, 8), (128, 192, 32), (200, 77, 40), (1000, 520, 128), (37, 5, 16)])
 def test_zgemm_sub(ops, M, N, K):
     import torch

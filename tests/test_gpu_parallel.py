@@ -54,6 +54,12 @@ def _worker(rank, world, port, out_dir):
         dens1 = out["density"][1] if rank == 0 else None
         u = par.uscat_sharded(c, centers=CEN, radii=RAD, k=float(KS[1]), eta=1.0, n_end=N_END, density=dens1,
                               density_shape=(3, N_END * N_END), x_grid=_grid())
+        # assembly of one system by block rows (bhs_assemble_rows) + all-gather of the strips: equals the unsharded matrix
+        from biem_helmholtz_sphere_b200 import _ops
+
+        A = par.assemble_sharded(c, centers=CEN, radii=RAD, k=1.7, eta=0.9, n_end=N_END, alpha=1.0, beta=0.2 + 0.1j)
+        A1 = _ops.assemble(3, N_END, CEN, RAD, np.array([1.7]), np.array([0.9]), np.full(3, 1.0 + 0j), np.full(3, 0.2 + 0.1j))[0]
+        assert A.shape == A1.shape and torch.equal(A.to(A1.device), A1)
         np.savez(os.path.join(out_dir, f"r{rank}.npz"), density=out["density"].cpu().numpy(),
                  uscat=out["uscat"].cpu().numpy(), field=u.cpu().numpy())
     finally:

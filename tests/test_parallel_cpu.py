@@ -70,6 +70,16 @@ def _oracle_eval_tile(c, centers, radii, k, eta, n_end, density, x_tile):
     return torch.as_tensor(res.uscat(np.asarray(x_tile)))
 
 
+def _oracle_assemble_rows(c, centers, radii, k, eta, n_end, alpha, beta, b_lo, b_hi):
+    from oracle import biem_oracle as O
+
+    B = len(radii)
+    A = O.assemble(c, np.asarray(centers), np.asarray(radii), k, n_end, eta, np.broadcast_to(np.asarray(alpha, complex), (B,)),
+                   np.broadcast_to(np.asarray(beta, complex), (B,)))  # [B, H, B, H]
+    H = A.shape[1]
+    return torch.as_tensor(A.reshape(B * H, B * H)[b_lo * H : b_hi * H].copy())
+
+
 def _worker(rank, world, port, K, out_dir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -89,6 +99,15 @@ def _worker(rank, world, port, K, out_dir):
         dens0 = out["density"][j] if rank == 0 else None
         u = par.uscat_sharded("a", centers=cen, radii=rad, k=float(ks[j]), eta=1.0, n_end=5, density=dens0,
                               density_shape=tuple(out["density"][j].shape), x_grid=grid, eval_tile=_oracle_eval_tile)
+        # (2b) assembly of one system by block rows + all-gather of the strips
+        A = par.assemble_sharded("a", centers=cen, radii=rad, k=1.4, eta=1.0, n_end=5, alpha=1.0, beta=0.3,
+                                 assemble_rows=_oracle_assemble_rows)
+        A_ref = _oracle_assemble_rows("a", cen, rad, 1.4, 1.0, 5, 1.0, 0.3, 0, 3)
+        assert A.shape == A_ref.shape and torch.equal(A, A_ref)
+        strip = par.assemble_sharded("a", centers=cen, radii=rad, k=1.4, eta=1.0, n_end=5, gather=False,
+                                     assemble_rows=_oracle_assemble_rows)
+        lo, hi = par.ball_rows(3, rank, world)
+        assert strip.shape[0] == (hi - lo) * 9
         # (3) local-only mode
         loc = par.sweep("a", centers=cen, radii=rad, ks=ks, n_end=5, eta=1.0, x=None, gather=False,
                         solve_shard=_oracle_solve_shard)
