@@ -38,6 +38,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+METRIC = "3D 16-sphere k-sweep systems/sec (assemble+solve)"  # first half of BASELINE.json's metric; `uscat` carries the second
 N_END = 16
 HALF = 2
 N_SYSTEMS = 256
@@ -163,7 +164,7 @@ def run_reference(args) -> None:
     cores = os.cpu_count()
     sample = f"{per_step} system(s) of the {args.systems}-k sweep per step, oracle (NumPy/SciPy, LAPACK zgesv, BLAS threads = all cores)"
     print(json.dumps({
-        "impl": "reference", "metric": "systems_per_sec", "value": value, "unit": "systems/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "systems/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": warm_done, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": _config(args.systems, args.gpus),
@@ -298,7 +299,7 @@ def run_b200(args) -> None:
     assert np.allclose(dd, np.asarray(dens_h), rtol=1e-12, atol=1e-14)
 
     out = {
-        "metric": "systems_per_sec", "value": value, "unit": "systems/s", "n_gpus": world, "steps": args.steps,
+        "metric": METRIC, "value": value, "unit": "systems/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": _config(args.systems, world),
         "e2e": {"value": e2e_value, "unit": "systems/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
@@ -500,7 +501,7 @@ def _bench_uscat(args, bhs, _ops, torch, dev, rank, world, barrier, dist):
     Ptot = G * G
     flops = 8.0 * Ptot * B * H
     return {
-        "metric": "uscat_points_per_sec", "value": Ptot / (ms * 1e-3), "unit": "points/s", "ms": ms,
+        "metric": "uscat points/sec (second half of BASELINE.json's metric)", "value": Ptot / (ms * 1e-3), "unit": "points/s", "ms": ms,
         "workload": f"C5: 64 unit spheres (8x8 grid), n_end=24 (H=576), k=1, {G}x{G} field grid on x2=0 over [-20,20]^2, "
                     f"rows split over {world} rank(s); synthetic density",
         "e2e": {"value": Ptot / (float(te[0]) * 1e-3), "unit": "points/s", "h2d_bytes": int(24 * Ptot), "d2h_bytes": int(16 * Ptot)},
