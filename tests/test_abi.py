@@ -49,3 +49,19 @@ def test_argument_validation_without_gpu():
         _lib.check(-1)
     with pytest.raises(NotImplementedError):
         _lib.check(-2)
+
+
+def test_header_is_valid_c_and_cxx(tmp_path):
+    """include/bhs.h is the drop-in boundary: it must compile as plain C (gcc) and as C++ (g++) on its own."""
+    import shutil
+    import subprocess
+
+    hdr = os.path.join(ROOT, "include", "bhs.h")
+    for cc, lang, std in (("gcc", "c", "-std=c99"), ("g++", "c++", "-std=c++11")):
+        if shutil.which(cc) is None:
+            pytest.skip(f"{cc} not available")
+        src = tmp_path / ("t." + ("c" if lang == "c" else "cpp"))
+        src.write_text('#include "bhs.h"\nint main(void) { int (*f)(void) = bhs_version; (void)f; return 0; }\n')
+        r = subprocess.run([cc, std, "-Wall", "-Werror", "-pedantic", "-fsyntax-only", f"-I{os.path.dirname(hdr)}", str(src)],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
