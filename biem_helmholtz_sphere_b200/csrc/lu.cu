@@ -18,6 +18,7 @@
 #define LU_NB 32     // panel width
 #define LU_NBO 128   // outer block width
 #define LU_R 128     // rows per tournament CTA
+#define LU_DBLK (LU_NB * LU_NB + 16)  // complex slots per system: factored diagonal block + the panel's net row map (64 ints)
 #define G_TM 64
 #define G_TN 64
 #define G_KC 8
@@ -217,13 +218,48 @@ __device__ __forceinline__ cplx crecip_fast(cplx p) {
     return crecip(p);
 }
 
-// One elimination step costs ONE block barrier: every warp finds its own best row with three warp-wide reductions
-// (the magnitude's bit pattern is a monotone 64-bit key), that row's owner publishes the row and its reciprocal pivot in
-// the warp's slot of a double-buffered shared array, and after the barrier every thread picks the winning warp's slot.
-__global__ void __launch_bounds__(LU_R) lu_select_kernel(const cplx* __restrict__ A, int64_t ld, int64_t col0, int w,
-                                                         const int32_t* __restrict__ rows_in, int64_t n_in,
-                                                         int64_t row_begin, int64_t row_end,
-                                                         int32_t* __restrict__ rows_out, SelectFinal fin, LuBatch bs) {
+// Warp-wide maximum of a 64-bit key and the lowest lane that holds it.  One reduction on the high words settles it unless
+// several lanes share the maximal high word (for magnitude keys: the top 20 mantissa bits agree -- rare), in which case the
+// low words decide.
+__device__ __forceinline__ unsigned long long warp_argmax_u64(unsigned long long key, int& lane_out) {
+    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+    const bool cand = hi == mhi;
+    unsigned vote = __ballot_sync(0xffffffffu, cand);
+    unsigned mlo;
+    if (__popc(vote) > 1) {
+        mlo = __reduce_max_sync(0xffffffffu, cand ? lo : 0u);
+        vote = __ballot_sync(0xffffffffu, cand && lo == mlo);
+        lane_out = __ffs(vote) - 1;
+    } else {
+        lane_out = __ffs(vote) - 1;
+        mlo = __shfl_sync(0xffffffffu, lo, lane_out);
+    }
+    return ((unsigned long long)mhi << 32) | mlo;
+}
+
+// One elimination step costs ONE block barrier: every warp finds its own best row with warp-wide reductions (the
+// magnitude's bit pattern is a monotone 64-bit key), that row's owners publish the row and its reciprocal pivot in the
+// warp's slot of a double-buffered shared array, and after the barrier every thread picks the winning warp's slot.
+//
+// Layout: SEL_Q lanes per candidate row (lane g of the group holds the columns = g mod SEL_Q).  The step loop is ROLLED
+// over groups of SEL_Q columns and the registers ROTATE by one local column per group, so that every register index is
+// static: in group cb, x[i] holds the column SEL_Q * ((cb + i) mod (32 / SEL_Q)) + g, the pivot columns of the group are
+// the x[0] of lanes g = 0 .. SEL_Q - 1 in turn, and finished columns (multipliers) travel round the back.  (The first
+// version was fully unrolled: 257 KB of straight-line SASS run once per CTA, 54 % of its stall samples in "no
+// instruction" under ncu.)  Candidate order, tie-breaking and every FMA are the same for every SEL_Q, so the pivots are too.
+//
+// Two instances.  SEL_Q = 4 (8 rows per warp, 16 warps) serves a lone system: a quarter of the dependent work per lane
+// and four warps per scheduler; together with lu_permute_kernel it takes an N = 4096 factorisation from 43 ms to 34 ms
+// (34 us instead of 41 us per tournament round; the chain of reductions, barrier and multiplier is what is left).
+// SEL_Q = 1 (one lane per row, 4 warps, 168 registers) serves systems factorised in lock step inside a sweep, where the
+// panels of other systems share the SMs with the tensor-core updates and the instruction count matters more than the
+// latency: the quad form there gave 140 systems/s against 147.
+template <int SEL_Q>
+__global__ void __launch_bounds__(LU_R * SEL_Q, SEL_Q == 1 ? 3 : 1)
+    lu_select_kernel(const cplx* __restrict__ A, int64_t ld, int64_t col0, int w, const int32_t* __restrict__ rows_in,
+                     int64_t n_in, int64_t row_begin, int64_t row_end, int32_t* __restrict__ rows_out, SelectFinal fin,
+                     LuBatch bs) {
     A += (int64_t)blockIdx.z * bs.sA;
     if (rows_in) rows_in += (int64_t)blockIdx.z * bs.sCand;
     rows_out += (int64_t)blockIdx.z * bs.sCand;
@@ -232,16 +268,18 @@ __global__ void __launch_bounds__(LU_R) lu_select_kernel(const cplx* __restrict_
         fin.info += blockIdx.z;
         fin.dblk += (int64_t)blockIdx.z * bs.sDblk;
     }
-    constexpr int NW = LU_R / 32;
+    constexpr int SEL_LC = LU_NB / SEL_Q, SEL_THREADS = LU_R * SEL_Q;
+    constexpr int NW = SEL_THREADS / 32;
     __shared__ cplx prow[2][NW][LU_NB];
     __shared__ cplx prinv[2][NW];
     __shared__ unsigned long long wkey[2][NW];
-    __shared__ int wlane[2][NW];
+    __shared__ int wquad[2][NW];
     __shared__ int32_t s_win[LU_NB];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane & (SEL_Q - 1), quad = lane / SEL_Q;
     const bool is_final = fin.ipiv != nullptr;
-    // which global row does this thread own?
-    int64_t slot = (int64_t)blockIdx.x * LU_R + tid;
+    // which global row does this quad own?
+    int64_t slot = (int64_t)blockIdx.x * LU_R + warp * (32 / SEL_Q) + quad;
     int32_t myrow = -1;
     if (rows_in) {
         if (slot < n_in) myrow = rows_in[slot];
@@ -249,109 +287,196 @@ __global__ void __launch_bounds__(LU_R) lu_select_kernel(const cplx* __restrict_
         int64_t r = row_begin + slot;
         if (r < row_end) myrow = (int32_t)r;
     }
-    // Each thread reads its own candidate row straight into registers (512 contiguous bytes per thread).  No
+    // The candidate row goes straight into registers (a quad reads 64 contiguous bytes per instruction).  No
     // shared-memory staging: a 67 KB tile would keep a second zgemm CTA of a concurrent system off this SM.
-    cplx x[LU_NB];
+    cplx x[SEL_LC];
     {
-        const cplx* src = A + (int64_t)(myrow >= 0 ? myrow : 0) * ld + col0;
+        const cplx* src = A + (int64_t)(myrow >= 0 ? myrow : 0) * ld + col0 + g;
 #pragma unroll
-        for (int c = 0; c < LU_NB; ++c) x[c] = (myrow >= 0 && c < w) ? __ldg(src + c) : cmake(0.0, 0.0);
+        for (int i = 0; i < SEL_LC; ++i) x[i] = (myrow >= 0 && SEL_Q * i + g < w) ? __ldg(src + SEL_Q * i) : cmake(0.0, 0.0);
     }
     bool active = myrow >= 0;
+    if (tid < LU_NB && tid >= w) {  // columns beyond a narrow (tail) panel select nothing
+        rows_out[(int64_t)blockIdx.x * LU_NB + tid] = -1;
+        s_win[tid] = -1;
+    }
+    const int ncb = (w + SEL_Q - 1) / SEL_Q;
+#pragma unroll 1
+    for (int cb = 0; cb < ncb; ++cb) {
 #pragma unroll
-    for (int c = 0; c < LU_NB; ++c) {
-        if (c < w) {
-            const int buf = c & 1;
-            // key: 0 = no candidate, otherwise 1 + bits(|re| + |im|)  (monotone in the magnitude)
-            const double mag = fabs(x[c].x) + fabs(x[c].y);
-            const unsigned long long key = active ? (unsigned long long)__double_as_longlong(mag) + 1ULL : 0ULL;
-            const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
-            const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
-            const bool cand = hi == mhi;
-            const unsigned mlo = __reduce_max_sync(0xffffffffu, cand ? lo : 0u);
-            const unsigned vote = __ballot_sync(0xffffffffu, cand && lo == mlo);
-            const int bl = __ffs(vote) - 1;
-            if (lane == bl) {
-                wkey[buf][warp] = key;
-                wlane[buf][warp] = bl;
-                if (key) {
+        for (int gg = 0; gg < SEL_Q; ++gg) {
+            const int c = SEL_Q * cb + gg;
+            if (c < w) {
+                const int buf = c & 1;
+                // key: 0 = no candidate, otherwise 1 + bits(|re| + |im|)  (monotone in the magnitude)
+                const double mag = fabs(x[0].x) + fabs(x[0].y);
+                const unsigned long long key =
+                    (active && g == gg) ? (unsigned long long)__double_as_longlong(mag) + 1ULL : 0ULL;
+                int bl;
+                const unsigned long long wbest = warp_argmax_u64(key, bl);
+                // this row's entry in the pivot column, for the whole quad (the multiplier needs it after the barrier)
+                cplx xc;
+                xc.x = __shfl_sync(0xffffffffu, x[0].x, (lane & ~(SEL_Q - 1)) | gg);
+                xc.y = __shfl_sync(0xffffffffu, x[0].y, (lane & ~(SEL_Q - 1)) | gg);
+                if (quad == bl / SEL_Q) {
+                    if (lane == bl) {
+                        wkey[buf][warp] = wbest;
+                        wquad[buf][warp] = quad;
+                        if (wbest) prinv[buf][warp] = wbest > 1ULL ? crecip_fast(x[0]) : cmake(0.0, 0.0);
+                    }
+                    if (wbest) {
 #pragma unroll
-                    for (int j = c; j < LU_NB; ++j) prow[buf][warp][j] = x[j];
-                    prinv[buf][warp] = key > 1ULL ? crecip_fast(x[c]) : cmake(0.0, 0.0);
+                        for (int i = 0; i < SEL_LC; ++i) prow[buf][warp][SEL_Q * i + g] = x[i];  // rotated like x
+                    }
+                }
+                __syncthreads();
+                // best warp: the same three reductions over the per-warp keys (lanes q and q + NW hold warp q's key; the
+                // lowest warp wins a tie, as the lowest lane does inside a warp)
+                int bw;
+                const unsigned long long best = warp_argmax_u64(wkey[buf][lane & (NW - 1)], bw);
+                const bool any = best != 0ULL;       // at least one active row left
+                const bool nonzero = best > 1ULL;    // its pivot entry is not exactly zero
+                if (any && warp == bw && quad == wquad[buf][bw]) {
+                    if (g == gg) {
+                        rows_out[(int64_t)blockIdx.x * LU_NB + c] = myrow;
+                        s_win[c] = myrow;
+                        if (is_final && !nonzero) atomicCAS(fin.info, 0, (int)(fin.j + c + 1));
+                    }
+                    if (is_final) {
+#pragma unroll
+                        for (int i = 0; i < SEL_LC; ++i)
+                            fin.dblk[c * LU_NB + SEL_Q * ((cb + i) & (SEL_LC - 1)) + g] = x[i];
+                    }
+                    active = false;
+                }
+                if (!any && tid == 0) { rows_out[(int64_t)blockIdx.x * LU_NB + c] = -1; s_win[c] = -1; }
+                if constexpr (SEL_Q == 1) {
+                    // one lane per row: eliminate and rotate in one pass (the multiplier goes to the back)
+                    const bool upd = any && active && nonzero;
+                    const cplx l = upd ? cmul(xc, prinv[buf][bw]) : x[0];
+                    const cplx ml = cmake(-l.x, -l.y);
+                    const cplx* pr = prow[buf][bw];
+                    const int live = upd ? (LU_NB - 1 - c) : 0;
+#pragma unroll
+                    for (int i = 1; i < LU_NB; ++i) {
+                        if (i <= live) x[i - 1] = cfma(ml, pr[i], x[i]);
+                        else x[i - 1] = x[i];
+                    }
+                    x[LU_NB - 1] = l;
+                } else if (any && active && nonzero) {
+                    const cplx l = cmul(xc, prinv[buf][bw]);
+                    const cplx ml = cmake(-l.x, -l.y);
+                    const cplx* pr = prow[buf][bw];
+                    // the group's own columns: the pivot column receives the multiplier (part of the factored diagonal
+                    // block if this row pivots later), the columns right of it are updated, those left of it are done
+                    if (g == gg) x[0] = l;
+                    else if (g > gg) x[0] = cfma(ml, pr[g], x[0]);
+#pragma unroll
+                    for (int i = 1; i < SEL_LC; ++i)
+                        if (cb + i < SEL_LC) x[i] = cfma(ml, pr[SEL_Q * i + g], x[i]);
                 }
             }
-            __syncthreads();
-            int bw = 0;
-            unsigned long long best = wkey[buf][0];
+        }
+        if constexpr (SEL_Q > 1) {
+            // rotate: the group's columns are finished and go to the back
+            const cplx t = x[0];
 #pragma unroll
-            for (int q = 1; q < NW; ++q) {
-                const unsigned long long kq = wkey[buf][q];
-                if (kq > best) { best = kq; bw = q; }
-            }
-            const bool any = best != 0ULL;       // at least one active row left
-            const bool nonzero = best > 1ULL;    // its pivot entry is not exactly zero
-            const int winner = bw * 32 + wlane[buf][bw];
-            if (any && tid == winner) {
-                rows_out[(int64_t)blockIdx.x * LU_NB + c] = myrow;
-                s_win[c] = myrow;
-                if (is_final) {
-#pragma unroll
-                    for (int j = 0; j < LU_NB; ++j) fin.dblk[c * LU_NB + j] = x[j];
-                    if (!nonzero) atomicCAS(fin.info, 0, (int)(fin.j + c + 1));
-                }
-                active = false;
-            }
-            if (!any && tid == 0) { rows_out[(int64_t)blockIdx.x * LU_NB + c] = -1; s_win[c] = -1; }
-            if (any && active && nonzero) {
-                const cplx l = cmul(x[c], prinv[buf][bw]);
-                x[c] = l;  // multiplier: becomes part of the factored diagonal block if this row pivots later
-#pragma unroll
-                for (int j = c + 1; j < LU_NB; ++j) x[j] = cfma(cmake(-l.x, -l.y), prow[buf][bw][j], x[j]);
-            }
-        } else {
-            if (tid == 0) { rows_out[(int64_t)blockIdx.x * LU_NB + c] = -1; s_win[c] = -1; }
+            for (int i = 1; i < SEL_LC; ++i) x[i - 1] = x[i];
+            x[SEL_LC - 1] = t;
         }
     }
     if (is_final) {
+        // Ordered pivot rows -> LAPACK-style sequential swaps ipiv[j + c], in O(w) steps: rows from below the diagonal
+        // block are still at home when their turn comes; rows of the diagonal block may have been displaced by an earlier
+        // swap, so their current position (where_top) and the row held by each diagonal-block position (cont_top) are
+        // tracked.
+        __shared__ int32_t where_top[LU_NB], cont_top[LU_NB];
+        const int32_t j0 = (int32_t)fin.j;
+        if (tid < LU_NB) { where_top[tid] = j0 + tid; cont_top[tid] = j0 + tid; }
         __syncthreads();
         if (tid == 0) {
-            // ordered pivot rows -> sequential swaps (follow the earlier swaps of this panel)
-            int32_t piv[LU_NB];
             for (int c = 0; c < w; ++c) {
-                int32_t loc = s_win[c];
-                if (loc < 0) loc = (int32_t)(fin.j + c);  // cannot happen for a square matrix; keep the row in place
-                for (int q = 0; q < c; ++q) {
-                    int32_t a0 = (int32_t)(fin.j + q), b0 = piv[q];
-                    if (loc == a0) loc = b0;
-                    else if (loc == b0) loc = a0;
+                const int32_t r = s_win[c];
+                int32_t loc = j0 + c;  // r < 0 cannot happen for a square matrix; keep the row in place
+                if (r >= 0) {
+                    loc = (r < j0 + w) ? where_top[r - j0] : r;
+                    const int32_t d = cont_top[c];  // always a row of the diagonal block
+                    where_top[d - j0] = loc;
+                    if (loc < j0 + w) cont_top[loc - j0] = d;
+                    if (r < j0 + w) where_top[r - j0] = j0 + c;
                 }
-                piv[c] = loc;
                 fin.ipiv[fin.j + c] = loc;
             }
+        }
+        __syncthreads();
+        // net effect of those swaps, for lu_permute_kernel: position j + q receives row s_win[q]; a row j + t of the
+        // diagonal block that was pushed out ends at where_top[t] >= j + w
+        int32_t* pmap = (int32_t*)(fin.dblk + LU_NB * LU_NB);
+        if (tid < LU_NB) {
+            pmap[tid] = (tid < w && s_win[tid] >= 0) ? s_win[tid] : j0 + tid;
+            pmap[LU_NB + tid] = (tid < w && where_top[tid] >= j0 + w) ? where_top[tid] : -1;
         }
     }
 }
 
-// Apply the swaps of one panel to `ncols` contiguous columns of a row-major array (matrix or rhs).
-// With `dblk` (matrix only) the panel's own columns [j, j+w) of rows [j, j+w) then receive the factored diagonal
-// block produced by the last tournament round.
-__global__ void lu_swap_kernel(cplx* __restrict__ M, int64_t ld, int64_t ncols, const int32_t* __restrict__ ipiv,
-                               int64_t j, int w, const cplx* __restrict__ dblk, int64_t sM, int64_t sIpiv, int64_t sDblk) {
-    M += (int64_t)blockIdx.z * sM;
-    ipiv += (int64_t)blockIdx.z * sIpiv;
-    if (dblk) dblk += (int64_t)blockIdx.z * sDblk;
-    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= ncols) return;
-    for (int q = 0; q < w; ++q) {
-        int64_t a = j + q, b = ipiv[j + q];
-        if (a != b) {
-            cplx va = M[a * ld + c], vb = M[b * ld + c];
-            M[a * ld + c] = vb;
-            M[b * ld + c] = va;
+// Apply the row interchanges of one panel to the matrix (and, in the same launch, to the right-hand sides) from the
+// panel's NET row map: all the rows of the diagonal block go through a shared-memory tile, so that every global load
+// is independent (the LAPACK-style sequence of 32 swaps is a chain of 32 dependent round trips per column).  64
+// columns per CTA, 4 threads per column.  The panel's own columns [j, j+w) of rows [j, j+w) receive the factored
+// diagonal block produced by the last tournament round.
+#define PERM_COLS 64
+__global__ void __launch_bounds__(256) lu_permute_kernel(cplx* __restrict__ M, int64_t ld, int64_t ncols, int nct,
+                                                         cplx* __restrict__ rhs, int nrhs, int64_t j, int w,
+                                                         const cplx* __restrict__ dblk, int64_t sM, int64_t sRhs,
+                                                         int64_t sDblk) {
+    __shared__ cplx tile[LU_NB][PERM_COLS];
+    __shared__ int32_t s_map[2 * LU_NB];
+    dblk += (int64_t)blockIdx.z * sDblk;
+    const int32_t* pmap = (const int32_t*)(dblk + LU_NB * LU_NB);
+    int64_t c0 = (int64_t)blockIdx.x * PERM_COLS;
+    if ((int)blockIdx.x >= nct) {  // right-hand-side columns
+        M = rhs + (int64_t)blockIdx.z * sRhs;
+        ld = nrhs;
+        ncols = nrhs;
+        c0 = (int64_t)((int)blockIdx.x - nct) * PERM_COLS;
+        dblk = nullptr;
+    } else {
+        M += (int64_t)blockIdx.z * sM;
+    }
+    const int tid = threadIdx.x, col = tid & (PERM_COLS - 1), q0 = (tid / PERM_COLS) * (LU_NB / 4);
+    const int64_t c = c0 + col;
+    const bool valid = c < ncols;
+    if (tid < 2 * LU_NB) s_map[tid] = pmap[tid];
+    if (valid) {
+#pragma unroll
+        for (int i = 0; i < LU_NB / 4; ++i)
+            if (q0 + i < w) tile[q0 + i][col] = M[(j + q0 + i) * ld + c];
+    }
+    __syncthreads();
+    cplx v[LU_NB / 4];
+    if (valid) {
+#pragma unroll
+        for (int i = 0; i < LU_NB / 4; ++i) {
+            const int q = q0 + i;
+            if (q < w) {
+                const int64_t src = s_map[q];
+                v[i] = (src < j + w) ? tile[src - j][col] : M[src * ld + c];
+            }
         }
     }
-    if (dblk && c >= j && c < j + w)
-        for (int q = 0; q < w; ++q) M[(j + q) * ld + c] = dblk[q * LU_NB + (c - j)];
+    __syncthreads();  // the rows read above are overwritten below, possibly by another thread of the column
+    if (valid) {
+        const bool in_panel = dblk != nullptr && c >= j && c < j + w;
+#pragma unroll
+        for (int i = 0; i < LU_NB / 4; ++i) {
+            const int q = q0 + i;
+            if (q < w) {
+                M[(j + q) * ld + c] = in_panel ? dblk[q * LU_NB + (c - j)] : v[i];
+                const int64_t dst = s_map[LU_NB + q];
+                if (dst >= 0) M[dst * ld + c] = tile[q][col];
+            }
+        }
+    }
 }
 
 // L21 = A21 U11^{-1}: one row per thread (registers), U11 in shared memory.  Also emits the packed
@@ -560,7 +685,7 @@ static LuWork lu_carve(int64_t N, int nbatch, void* base) {
     w.ncand = cdiv64(N, LU_R) * LU_NB + LU_NB;
     w.cand0 = (int32_t*)take(w.ncand * 4 * nbatch);
     w.cand1 = (int32_t*)take(w.ncand * 4 * nbatch);
-    w.dblk = (cplx*)take((int64_t)LU_NB * LU_NB * sizeof(cplx) * nbatch);
+    w.dblk = (cplx*)take((int64_t)LU_DBLK * sizeof(cplx) * nbatch);
     int64_t rtiles = cdiv64(N, G_TM) + 1, ctiles = cdiv64(N, G_TN) + 1;
     int nks = LU_NBO / G_KC;
     w.sLp = rtiles * nks * G_A_STAGE;
@@ -634,24 +759,31 @@ static void lu_panel(LuCtx& x, int64_t j, int w) {
     int cur = 0;
     bhs_prof_begin(BHS_PROF_LU_PANEL, x.st);
     const SelectFinal fin{j, x.ipiv, x.info, x.dblk}, nofin{0, nullptr, nullptr, nullptr};
-    lu_select_kernel<<<dim3((unsigned)nsets, 1, x.nbatch), LU_R, 0, x.st>>>(x.A, x.ld, j, w, nullptr, 0, j, x.N, x.cand[cur],
-                                                                            nsets == 1 ? fin : nofin, x.bs);
+    const bool quad = x.nbatch == 1;  // lanes per candidate row: 4 for a lone system (latency), 1 in a sweep (throughput)
+    if (quad)
+        lu_select_kernel<4><<<dim3((unsigned)nsets, 1, x.nbatch), LU_R * 4, 0, x.st>>>(x.A, x.ld, j, w, nullptr, 0, j, x.N, x.cand[cur],
+                                                                                   nsets == 1 ? fin : nofin, x.bs);
+    else
+        lu_select_kernel<1><<<dim3((unsigned)nsets, 1, x.nbatch), LU_R, 0, x.st>>>(x.A, x.ld, j, w, nullptr, 0, j, x.N, x.cand[cur],
+                                                                               nsets == 1 ? fin : nofin, x.bs);
     LU_LAUNCH_CHECK(x);
     while (nsets > 1) {
         int64_t n_in = nsets * LU_NB;
         int64_t nsets2 = cdiv64(n_in, LU_R);
-        lu_select_kernel<<<dim3((unsigned)nsets2, 1, x.nbatch), LU_R, 0, x.st>>>(x.A, x.ld, j, w, x.cand[cur], n_in, 0, 0,
-                                                                                 x.cand[cur ^ 1], nsets2 == 1 ? fin : nofin, x.bs);
+        if (quad)
+            lu_select_kernel<4><<<dim3((unsigned)nsets2, 1, x.nbatch), LU_R * 4, 0, x.st>>>(
+                x.A, x.ld, j, w, x.cand[cur], n_in, 0, 0, x.cand[cur ^ 1], nsets2 == 1 ? fin : nofin, x.bs);
+        else
+            lu_select_kernel<1><<<dim3((unsigned)nsets2, 1, x.nbatch), LU_R, 0, x.st>>>(
+                x.A, x.ld, j, w, x.cand[cur], n_in, 0, 0, x.cand[cur ^ 1], nsets2 == 1 ? fin : nofin, x.bs);
         LU_LAUNCH_CHECK(x);
         cur ^= 1;
         nsets = nsets2;
     }
-    lu_swap_kernel<<<dim3((unsigned)cdiv64(x.N, 256), 1, x.nbatch), 256, 0, x.st>>>(x.A, x.ld, x.N, x.ipiv, j, w, x.dblk, x.bs.sA,
-                                                                                    x.bs.sIpiv, x.bs.sDblk);
-    LU_LAUNCH_CHECK(x);
-    if (x.rhs) {
-        lu_swap_kernel<<<dim3((unsigned)cdiv64(x.nrhs, 32), 1, x.nbatch), 32, 0, x.st>>>(x.rhs, x.nrhs, x.nrhs, x.ipiv, j, w, nullptr,
-                                                                                         x.bs.sRhs, x.bs.sIpiv, 0);
+    {
+        const int nct = (int)cdiv64(x.N, PERM_COLS), nrt = x.rhs ? (int)cdiv64(x.nrhs, PERM_COLS) : 0;
+        lu_permute_kernel<<<dim3((unsigned)(nct + nrt), 1, x.nbatch), 256, 0, x.st>>>(x.A, x.ld, x.N, nct, x.rhs, x.nrhs, j, w, x.dblk,
+                                                                                      x.bs.sA, x.bs.sRhs, x.bs.sDblk);
         LU_LAUNCH_CHECK(x);
     }
     if (j + w < x.N) {
@@ -766,7 +898,7 @@ static int lu_setup(LuCtx& x, int64_t N, double* d_A, int64_t ld, double* d_rhs,
     LuWork w = lu_carve(N, nbatch, d_work);
     x.nbatch = nbatch;
     x.bs.sA = strideA; x.bs.sRhs = stride_rhs; x.bs.sIpiv = N; x.bs.sCand = w.ncand;
-    x.bs.sDblk = (int64_t)LU_NB * LU_NB; x.bs.sLp = w.sLp; x.bs.sUp = w.sUp;
+    x.bs.sDblk = (int64_t)LU_DBLK; x.bs.sLp = w.sLp; x.bs.sUp = w.sUp;
     x.A = (cplx*)d_A; x.ld = ld; x.N = N; x.rhs = (cplx*)d_rhs; x.nrhs = nrhs;
     x.ipiv = d_ipiv; x.info = d_info; x.cand[0] = w.cand0; x.cand[1] = w.cand1; x.dblk = w.dblk;
     x.Lp = w.Lp; x.Up = w.Up; x.nks_total = LU_NBO / G_KC; x.J = 0;

@@ -2,12 +2,9 @@
 
 Tolerances are written per test; floating point throughout (complex128), index tables bit-exact.
 """
-import math
-
 import numpy as np
 import pytest
 
-import oracle
 from oracle import biem_oracle as bo
 
 pytestmark = pytest.mark.gpu

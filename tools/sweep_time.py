@@ -1,4 +1,4 @@
-import torch, time, numpy as np, os, sys
+import torch, time, os, sys
 sys.path.insert(0, "/root/repo")
 import biem_helmholtz_sphere_b200 as bhs
 from biem_helmholtz_sphere_b200.geometry import grid_centers, sweep_wavenumbers

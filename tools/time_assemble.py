@@ -1,6 +1,6 @@
 """Time bhs_assemble alone at C3 (16 spheres, n_end 16) and C5 (64 spheres, n_end 24): best / median of 10 launches."""
 import os, sys
-import numpy as np, torch
+import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from biem_helmholtz_sphere_b200 import _ops
 from biem_helmholtz_sphere_b200.geometry import grid_centers
