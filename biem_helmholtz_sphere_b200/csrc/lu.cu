@@ -238,6 +238,41 @@ __device__ __forceinline__ unsigned long long warp_argmax_u64(unsigned long long
     return ((unsigned long long)mhi << 32) | mlo;
 }
 
+// Bookkeeping of the last tournament round (one CTA, all threads call it after their last step): LAPACK-style
+// sequential swaps ipiv[j + c] and the panel's net row map for lu_permute_kernel.
+__device__ __forceinline__ void select_finish(const SelectFinal& fin, int w, const int32_t* s_win, int tid) {
+    // Ordered pivot rows -> LAPACK-style sequential swaps ipiv[j + c], in O(w) steps: rows from below the diagonal
+    // block are still at home when their turn comes; rows of the diagonal block may have been displaced by an earlier
+    // swap, so their current position (where_top) and the row held by each diagonal-block position (cont_top) are
+    // tracked.
+    __shared__ int32_t where_top[LU_NB], cont_top[LU_NB];
+    const int32_t j0 = (int32_t)fin.j;
+    if (tid < LU_NB) { where_top[tid] = j0 + tid; cont_top[tid] = j0 + tid; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int c = 0; c < w; ++c) {
+            const int32_t r = s_win[c];
+            int32_t loc = j0 + c;  // r < 0 cannot happen for a square matrix; keep the row in place
+            if (r >= 0) {
+                loc = (r < j0 + w) ? where_top[r - j0] : r;
+                const int32_t d = cont_top[c];  // always a row of the diagonal block
+                where_top[d - j0] = loc;
+                if (loc < j0 + w) cont_top[loc - j0] = d;
+                if (r < j0 + w) where_top[r - j0] = j0 + c;
+            }
+            fin.ipiv[fin.j + c] = loc;
+        }
+    }
+    __syncthreads();
+    // net effect of those swaps, for lu_permute_kernel: position j + q receives row s_win[q]; a row j + t of the
+    // diagonal block that was pushed out ends at where_top[t] >= j + w
+    int32_t* pmap = (int32_t*)(fin.dblk + LU_NB * LU_NB);
+    if (tid < LU_NB) {
+        pmap[tid] = (tid < w && s_win[tid] >= 0) ? s_win[tid] : j0 + tid;
+        pmap[LU_NB + tid] = (tid < w && where_top[tid] >= j0 + w) ? where_top[tid] : -1;
+    }
+}
+
 // One elimination step costs ONE block barrier: every warp finds its own best row with warp-wide reductions (the
 // magnitude's bit pattern is a monotone 64-bit key), that row's owners publish the row and its reciprocal pivot in the
 // warp's slot of a double-buffered shared array, and after the barrier every thread picks the winning warp's slot.
@@ -249,14 +284,12 @@ __device__ __forceinline__ unsigned long long warp_argmax_u64(unsigned long long
 // version was fully unrolled: 257 KB of straight-line SASS run once per CTA, 54 % of its stall samples in "no
 // instruction" under ncu.)  Candidate order, tie-breaking and every FMA are the same for every SEL_Q, so the pivots are too.
 //
-// Two instances.  SEL_Q = 4 (8 rows per warp, 16 warps) serves a lone system: a quarter of the dependent work per lane
-// and four warps per scheduler; together with lu_permute_kernel it takes an N = 4096 factorisation from 43 ms to 34 ms
-// (34 us instead of 41 us per tournament round; the chain of reductions, barrier and multiplier is what is left).
-// SEL_Q = 1 (one lane per row, 4 warps, 168 registers) serves systems factorised in lock step inside a sweep, where the
-// panels of other systems share the SMs with the tensor-core updates and the instruction count matters more than the
-// latency: the quad form there gave 140 systems/s against 147.
+// SEL_Q = 4 (8 rows per warp, 16 warps) serves a lone system: a quarter of the dependent work per lane and four warps
+// per scheduler; together with lu_permute_kernel it takes an N = 4096 factorisation from 43 ms to 34 ms (34 us instead of
+// 41 us per tournament round; the chain of reductions, barrier and multiplier is what is left).  Systems factorised in
+// lock step inside a sweep use lu_select_unrolled_kernel below.
 template <int SEL_Q>
-__global__ void __launch_bounds__(LU_R * SEL_Q, SEL_Q == 1 ? 3 : 1)
+__global__ void __launch_bounds__(LU_R * SEL_Q)
     lu_select_kernel(const cplx* __restrict__ A, int64_t ld, int64_t col0, int w, const int32_t* __restrict__ rows_in,
                      int64_t n_in, int64_t row_begin, int64_t row_end, int32_t* __restrict__ rows_out, SelectFinal fin,
                      LuBatch bs) {
@@ -350,20 +383,7 @@ __global__ void __launch_bounds__(LU_R * SEL_Q, SEL_Q == 1 ? 3 : 1)
                     active = false;
                 }
                 if (!any && tid == 0) { rows_out[(int64_t)blockIdx.x * LU_NB + c] = -1; s_win[c] = -1; }
-                if constexpr (SEL_Q == 1) {
-                    // one lane per row: eliminate and rotate in one pass (the multiplier goes to the back)
-                    const bool upd = any && active && nonzero;
-                    const cplx l = upd ? cmul(xc, prinv[buf][bw]) : x[0];
-                    const cplx ml = cmake(-l.x, -l.y);
-                    const cplx* pr = prow[buf][bw];
-                    const int live = upd ? (LU_NB - 1 - c) : 0;
-#pragma unroll
-                    for (int i = 1; i < LU_NB; ++i) {
-                        if (i <= live) x[i - 1] = cfma(ml, pr[i], x[i]);
-                        else x[i - 1] = x[i];
-                    }
-                    x[LU_NB - 1] = l;
-                } else if (any && active && nonzero) {
+                if (any && active && nonzero) {
                     const cplx l = cmul(xc, prinv[buf][bw]);
                     const cplx ml = cmake(-l.x, -l.y);
                     const cplx* pr = prow[buf][bw];
@@ -377,46 +397,112 @@ __global__ void __launch_bounds__(LU_R * SEL_Q, SEL_Q == 1 ? 3 : 1)
                 }
             }
         }
-        if constexpr (SEL_Q > 1) {
-            // rotate: the group's columns are finished and go to the back
-            const cplx t = x[0];
+        // rotate: the group's columns are finished and go to the back
+        const cplx t = x[0];
 #pragma unroll
-            for (int i = 1; i < SEL_LC; ++i) x[i - 1] = x[i];
-            x[SEL_LC - 1] = t;
-        }
+        for (int i = 1; i < SEL_LC; ++i) x[i - 1] = x[i];
+        x[SEL_LC - 1] = t;
     }
-    if (is_final) {
-        // Ordered pivot rows -> LAPACK-style sequential swaps ipiv[j + c], in O(w) steps: rows from below the diagonal
-        // block are still at home when their turn comes; rows of the diagonal block may have been displaced by an earlier
-        // swap, so their current position (where_top) and the row held by each diagonal-block position (cont_top) are
-        // tracked.
-        __shared__ int32_t where_top[LU_NB], cont_top[LU_NB];
-        const int32_t j0 = (int32_t)fin.j;
-        if (tid < LU_NB) { where_top[tid] = j0 + tid; cont_top[tid] = j0 + tid; }
-        __syncthreads();
-        if (tid == 0) {
-            for (int c = 0; c < w; ++c) {
-                const int32_t r = s_win[c];
-                int32_t loc = j0 + c;  // r < 0 cannot happen for a square matrix; keep the row in place
-                if (r >= 0) {
-                    loc = (r < j0 + w) ? where_top[r - j0] : r;
-                    const int32_t d = cont_top[c];  // always a row of the diagonal block
-                    where_top[d - j0] = loc;
-                    if (loc < j0 + w) cont_top[loc - j0] = d;
-                    if (r < j0 + w) where_top[r - j0] = j0 + c;
+    if (is_final) select_finish(fin, w, s_win, tid);
+}
+
+// One lane per candidate row, every step unrolled with static register indices (no rotation, no predicated-off work:
+// the fewest issued instructions, at the price of 257 KB of straight-line SASS).  Used for systems factorised in lock
+// step inside a sweep, where the panels of many systems share the SMs with the tensor-core updates: measured on the
+// same box, C3 sweep, 146.2 systems/s with this form against 145.2 with the rolled one-lane form and 140 with quads.
+__global__ void __launch_bounds__(LU_R) lu_select_unrolled_kernel(const cplx* __restrict__ A, int64_t ld, int64_t col0, int w,
+                                                         const int32_t* __restrict__ rows_in, int64_t n_in,
+                                                         int64_t row_begin, int64_t row_end,
+                                                         int32_t* __restrict__ rows_out, SelectFinal fin, LuBatch bs) {
+    A += (int64_t)blockIdx.z * bs.sA;
+    if (rows_in) rows_in += (int64_t)blockIdx.z * bs.sCand;
+    rows_out += (int64_t)blockIdx.z * bs.sCand;
+    if (fin.ipiv) {
+        fin.ipiv += (int64_t)blockIdx.z * bs.sIpiv;
+        fin.info += blockIdx.z;
+        fin.dblk += (int64_t)blockIdx.z * bs.sDblk;
+    }
+    constexpr int NW = LU_R / 32;
+    __shared__ cplx prow[2][NW][LU_NB];
+    __shared__ cplx prinv[2][NW];
+    __shared__ unsigned long long wkey[2][NW];
+    __shared__ int wlane[2][NW];
+    __shared__ int32_t s_win[LU_NB];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool is_final = fin.ipiv != nullptr;
+    // which global row does this thread own?
+    int64_t slot = (int64_t)blockIdx.x * LU_R + tid;
+    int32_t myrow = -1;
+    if (rows_in) {
+        if (slot < n_in) myrow = rows_in[slot];
+    } else {
+        int64_t r = row_begin + slot;
+        if (r < row_end) myrow = (int32_t)r;
+    }
+    // Each thread reads its own candidate row straight into registers (512 contiguous bytes per thread).  No
+    // shared-memory staging: a 67 KB tile would keep a second zgemm CTA of a concurrent system off this SM.
+    cplx x[LU_NB];
+    {
+        const cplx* src = A + (int64_t)(myrow >= 0 ? myrow : 0) * ld + col0;
+#pragma unroll
+        for (int c = 0; c < LU_NB; ++c) x[c] = (myrow >= 0 && c < w) ? __ldg(src + c) : cmake(0.0, 0.0);
+    }
+    bool active = myrow >= 0;
+#pragma unroll
+    for (int c = 0; c < LU_NB; ++c) {
+        if (c < w) {
+            const int buf = c & 1;
+            // key: 0 = no candidate, otherwise 1 + bits(|re| + |im|)  (monotone in the magnitude)
+            const double mag = fabs(x[c].x) + fabs(x[c].y);
+            const unsigned long long key = active ? (unsigned long long)__double_as_longlong(mag) + 1ULL : 0ULL;
+            const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+            const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+            const bool cand = hi == mhi;
+            const unsigned mlo = __reduce_max_sync(0xffffffffu, cand ? lo : 0u);
+            const unsigned vote = __ballot_sync(0xffffffffu, cand && lo == mlo);
+            const int bl = __ffs(vote) - 1;
+            if (lane == bl) {
+                wkey[buf][warp] = key;
+                wlane[buf][warp] = bl;
+                if (key) {
+#pragma unroll
+                    for (int j = c; j < LU_NB; ++j) prow[buf][warp][j] = x[j];
+                    prinv[buf][warp] = key > 1ULL ? crecip_fast(x[c]) : cmake(0.0, 0.0);
                 }
-                fin.ipiv[fin.j + c] = loc;
             }
-        }
-        __syncthreads();
-        // net effect of those swaps, for lu_permute_kernel: position j + q receives row s_win[q]; a row j + t of the
-        // diagonal block that was pushed out ends at where_top[t] >= j + w
-        int32_t* pmap = (int32_t*)(fin.dblk + LU_NB * LU_NB);
-        if (tid < LU_NB) {
-            pmap[tid] = (tid < w && s_win[tid] >= 0) ? s_win[tid] : j0 + tid;
-            pmap[LU_NB + tid] = (tid < w && where_top[tid] >= j0 + w) ? where_top[tid] : -1;
+            __syncthreads();
+            int bw = 0;
+            unsigned long long best = wkey[buf][0];
+#pragma unroll
+            for (int q = 1; q < NW; ++q) {
+                const unsigned long long kq = wkey[buf][q];
+                if (kq > best) { best = kq; bw = q; }
+            }
+            const bool any = best != 0ULL;       // at least one active row left
+            const bool nonzero = best > 1ULL;    // its pivot entry is not exactly zero
+            const int winner = bw * 32 + wlane[buf][bw];
+            if (any && tid == winner) {
+                rows_out[(int64_t)blockIdx.x * LU_NB + c] = myrow;
+                s_win[c] = myrow;
+                if (is_final) {
+#pragma unroll
+                    for (int j = 0; j < LU_NB; ++j) fin.dblk[c * LU_NB + j] = x[j];
+                    if (!nonzero) atomicCAS(fin.info, 0, (int)(fin.j + c + 1));
+                }
+                active = false;
+            }
+            if (!any && tid == 0) { rows_out[(int64_t)blockIdx.x * LU_NB + c] = -1; s_win[c] = -1; }
+            if (any && active && nonzero) {
+                const cplx l = cmul(x[c], prinv[buf][bw]);
+                x[c] = l;  // multiplier: becomes part of the factored diagonal block if this row pivots later
+#pragma unroll
+                for (int j = c + 1; j < LU_NB; ++j) x[j] = cfma(cmake(-l.x, -l.y), prow[buf][bw][j], x[j]);
+            }
+        } else {
+            if (tid == 0) { rows_out[(int64_t)blockIdx.x * LU_NB + c] = -1; s_win[c] = -1; }
         }
     }
+    if (is_final) select_finish(fin, w, s_win, tid);
 }
 
 // Apply the row interchanges of one panel to the matrix (and, in the same launch, to the right-hand sides) from the
@@ -759,13 +845,13 @@ static void lu_panel(LuCtx& x, int64_t j, int w) {
     int cur = 0;
     bhs_prof_begin(BHS_PROF_LU_PANEL, x.st);
     const SelectFinal fin{j, x.ipiv, x.info, x.dblk}, nofin{0, nullptr, nullptr, nullptr};
-    const bool quad = x.nbatch == 1;  // lanes per candidate row: 4 for a lone system (latency), 1 in a sweep (throughput)
+    const bool quad = x.nbatch == 1;  // 4 lanes per candidate row for a lone system (latency); unrolled one-lane form in a sweep
     if (quad)
         lu_select_kernel<4><<<dim3((unsigned)nsets, 1, x.nbatch), LU_R * 4, 0, x.st>>>(x.A, x.ld, j, w, nullptr, 0, j, x.N, x.cand[cur],
                                                                                    nsets == 1 ? fin : nofin, x.bs);
     else
-        lu_select_kernel<1><<<dim3((unsigned)nsets, 1, x.nbatch), LU_R, 0, x.st>>>(x.A, x.ld, j, w, nullptr, 0, j, x.N, x.cand[cur],
-                                                                               nsets == 1 ? fin : nofin, x.bs);
+        lu_select_unrolled_kernel<<<dim3((unsigned)nsets, 1, x.nbatch), LU_R, 0, x.st>>>(x.A, x.ld, j, w, nullptr, 0, j, x.N, x.cand[cur],
+                                                                                     nsets == 1 ? fin : nofin, x.bs);
     LU_LAUNCH_CHECK(x);
     while (nsets > 1) {
         int64_t n_in = nsets * LU_NB;
@@ -774,7 +860,7 @@ static void lu_panel(LuCtx& x, int64_t j, int w) {
             lu_select_kernel<4><<<dim3((unsigned)nsets2, 1, x.nbatch), LU_R * 4, 0, x.st>>>(
                 x.A, x.ld, j, w, x.cand[cur], n_in, 0, 0, x.cand[cur ^ 1], nsets2 == 1 ? fin : nofin, x.bs);
         else
-            lu_select_kernel<1><<<dim3((unsigned)nsets2, 1, x.nbatch), LU_R, 0, x.st>>>(
+            lu_select_unrolled_kernel<<<dim3((unsigned)nsets2, 1, x.nbatch), LU_R, 0, x.st>>>(
                 x.A, x.ld, j, w, x.cand[cur], n_in, 0, 0, x.cand[cur ^ 1], nsets2 == 1 ? fin : nofin, x.bs);
         LU_LAUNCH_CHECK(x);
         cur ^= 1;
