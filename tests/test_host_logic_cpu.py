@@ -72,3 +72,51 @@ def test_no_cpu_fallback():
     with pytest.raises(Exception) as ei:
         bhs.biem(c, k=np.asarray(1.0), n_end=3, centers=np.array([[0.0, 2.0, 0.0], [0.0, -2.0, 0.0]]), radii=np.ones(2))
     assert "CUDA" in str(ei.value) or "cuda" in str(ei.value)
+
+
+def test_panel_row_map_algorithm():
+    """Specification of the pivot bookkeeping of the last tournament round (csrc/lu.cu, select_finish): from the ordered list
+    of pivot rows of a panel it derives, in O(w) steps, the LAPACK-style sequential swaps ipiv[j + c] and the panel's net row
+    map used by lu_permute_kernel.  Restated here in Python and checked against literally applying the swaps."""
+    import random
+
+    def finish(j, w, s_win):
+        where = [j + t for t in range(32)]   # current position of diagonal-block row j + t
+        cont = [j + t for t in range(32)]    # row currently held by diagonal-block position j + t
+        piv = []
+        for c in range(w):
+            r = s_win[c]
+            loc = where[r - j] if r < j + w else r
+            d = cont[c]
+            where[d - j] = loc
+            if loc < j + w:
+                cont[loc - j] = d
+            if r < j + w:
+                where[r - j] = j + c
+            piv.append(loc)
+        src_top = [s_win[q] if q < w else j + q for q in range(32)]
+        dst_out = [where[t] if (t < w and where[t] >= j + w) else -1 for t in range(32)]
+        return piv, src_top, dst_out
+
+    rnd = random.Random(7)
+    for _ in range(3000):
+        w = rnd.choice([32, 32, 17, 5, 2, 1])
+        j = rnd.randrange(0, 50)
+        m = w if (w < 32 or rnd.random() < 0.1) else w + rnd.choice([1, 7, 64, 400])
+        s_win = rnd.sample(range(j, j + m), w)
+        if rnd.random() < 0.4:  # bias towards pivots that already sit in the diagonal block
+            s_win = [r if rnd.random() < 0.5 else j + q for q, r in enumerate(s_win)]
+            if len(set(s_win)) < w:
+                continue
+        piv, src_top, dst_out = finish(j, w, s_win)
+        rows = list(range(j + m))
+        for c, p in enumerate(piv):  # LAPACK semantics
+            rows[j + c], rows[p] = rows[p], rows[j + c]
+        assert rows[j : j + w] == s_win
+        net = list(range(j + m))
+        for q in range(w):
+            net[j + q] = src_top[q]
+        for t in range(w):
+            if dst_out[t] >= 0:
+                net[dst_out[t]] = j + t
+        assert net == rows
