@@ -198,7 +198,7 @@ __global__ void pack_u_kernel(const cplx* __restrict__ A, int64_t ld, int64_t nc
 // The LAST round of a panel (one CTA, fin.ipiv != nullptr) also finishes the panel's bookkeeping, so that no
 // single-thread / single-CTA kernels sit on the critical path:
 //   * the eliminated pivot rows ARE the factored diagonal block (multipliers left of the diagonal, U on and right of
-//     it): they are written to fin.dblk [w][LU_NB] and copied into A by the swap kernel;
+//     it): they are written to fin.dblk [w][LU_NB] and copied into A by lu_permute_kernel;
 //   * the ordered pivot list is converted to LAPACK-style sequential swaps ipiv[j + c];
 //   * a zero pivot sets info = j + c + 1.
 struct SelectFinal {
@@ -743,7 +743,7 @@ struct LuCtx {
     int32_t* ipiv;
     int32_t* info;
     int32_t* cand[2];
-    cplx* dblk;  // [LU_NB][LU_NB] factored diagonal block handed from the last tournament round to the swap kernel
+    cplx* dblk;  // [LU_NB][LU_NB] factored diagonal block handed from the last tournament round to lu_permute_kernel (+ the net row map)
     double* Lp;
     double* Up;
     int nks_total;      // LU_NBO / G_KC
