@@ -16,13 +16,16 @@ Deliberate differences from the reference (documented in DESIGN.md):
   as j + i y), j_n by Miller's algorithm -- oracle-pinned against scipy's complex-argument Bessel functions;
 * leading batch axes of ``k`` WORK together with ``uin`` (the reference raises there); the
   semantics are "identical to a loop of scalar-k calls";
-* extra keyword ``keep_matrix`` (default True = reference behaviour) lets sweeps drop the N x N matrices.
+* extra keyword ``keep_matrix`` (default True = reference behaviour) lets sweeps drop the N x N matrices;
+* an exactly singular system raises ``numpy.linalg.LinAlgError`` for NumPy callers (as the reference's solve does); for
+  torch callers its density is NaN instead (no host synchronisation inside a sweep).
 """
 
 from __future__ import annotations
 
 import contextlib
 import math
+import threading
 import warnings
 from collections.abc import Callable
 from typing import Any, Literal, NotRequired, Protocol, TypedDict
@@ -32,7 +35,7 @@ import numpy as np
 import torch
 
 from . import _ops
-from ._coords import branching_types_of
+from ._coords import tree_spec
 from ._lib import get_plan
 
 Array = Any
@@ -57,7 +60,16 @@ class _NS:
 
     def out(self, t: torch.Tensor):
         if self.kind == "numpy":
-            return t.detach().cpu().numpy()
+            t = t.detach()
+            nbytes = t.numel() * t.element_size()
+            if t.is_cuda and (1 << 20) <= nbytes <= (4 << 30):
+                # large results (the N x N matrices the reference returns by default): one asynchronous copy into pinned
+                # host memory from torch's caching host allocator instead of a pageable .cpu() (PCIe-rate, ~20x faster)
+                host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                host.copy_(t, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                return host.numpy()
+            return t.cpu().numpy()
         return t.to(self.device)
 
     def asuser(self, t: torch.Tensor):
@@ -177,7 +189,10 @@ class BIEMResultCalculator:
     kind: Literal["inner", "outer"]
     density: Array | None = None
     matrix: Array | None = None
-    _dev_state: dict = attrs.field(factory=dict, eq=False, repr=False)
+    # device-resident copies of the fields above, attached by biem() for the evaluation kernels.  Not an __init__
+    # argument: attrs.evolve(res, density=...) therefore builds a record WITHOUT it and biem_u falls back to the
+    # public fields, as the reference's biem_u always does.
+    _dev_state: dict = attrs.field(factory=dict, eq=False, repr=False, init=False)
 
     def uscat(self, x: Array, /, far_field: bool = False, per_ball: bool = False, expand_x: bool = True) -> Array:
         return biem_u(self, x, far_field=far_field, per_ball=per_ball, expand_x=expand_x)
@@ -186,8 +201,7 @@ class BIEMResultCalculator:
 # --------------------------------------------------------------------------------------------------
 # input checks (mirror of _check_biem_inputs, _biem.py:240-326)
 # --------------------------------------------------------------------------------------------------
-def _check_biem_inputs(bt: str, centers, radii, k, eta, alpha, beta):
-    d = len(bt) + 1
+def _check_biem_inputs(d: int, centers, radii, k, eta, alpha, beta):
     cen = _t(centers)
     rad = _t(radii)
     kk = _t(k)
@@ -349,7 +363,6 @@ class _Slot:
         self.bufs = _ops.SolveBuffers(N, 1, S)
         self.work = _ops._work(_ops.load().bhs_assemble_workspace(plan.handle, B, S))
         self.graph: torch.cuda.CUDAGraph | None = None
-        self.warm = False
 
 
 class SweepEngine:
@@ -378,6 +391,8 @@ class SweepEngine:
         self.slots = [_Slot(d, n_end, B, self.N, batch) for _ in range(nslots)]
         self.slot_bytes = nslots * batch * 16 * self.N * self.N
         self.use_graphs = use_graphs
+        self.graphs_ready = False
+        self.lock = threading.Lock()  # one sweep at a time per engine (slots, streams and graphs are shared state)
 
     def _assemble(self, s: _Slot) -> None:
         _ops.assemble(self.d, self.n_end, self.cen, self.rad, s.k, s.eta, self.al, self.be, out=s.A, work=s.work,
@@ -393,10 +408,35 @@ class SweepEngine:
         self.al.copy_(al)
         self.be.copy_(be)
 
-    def run(self, ks, etas, f_hat, out_density, out_matrix=None, kis=None) -> None:
-        """ks, etas (and kis = Im k for a complex_k engine): [K]; f_hat: [K, N]; out_density: [K, N]; out_matrix: [K, N, N] or None."""
+    def _ensure_graphs(self) -> None:
+        """One eager pass on slot 0 (loads every kernel and sets the function attributes), then the (assembly -> LU)
+        sequence of EVERY slot is captured up front -- before any copy or solve of the sweep is enqueued, so that the
+        device-wide synchronisations of graph capture never stall groups in flight.  `thread_local` capture mode: CUDA
+        calls of other host threads (a pinning DataLoader thread, a second engine) do not invalidate the capture."""
+        if self.graphs_ready or not self.use_graphs:
+            return
+        s0 = self.slots[0]
+        with torch.cuda.stream(s0.stream):
+            self._body(s0)
+        s0.stream.synchronize()
+        for s in self.slots:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=s.stream, capture_error_mode="thread_local"):
+                self._body(s)
+            s.graph = g
+        self.graphs_ready = True
+
+    def run(self, ks, etas, f_hat, out_density, out_matrix=None, kis=None, out_info=None) -> None:
+        """ks, etas (and kis = Im k for a complex_k engine): [K]; f_hat: [K, N]; out_density: [K, N]; out_matrix: [K, N, N]
+        or None; out_info: int32 [K] or None (zero-pivot flag of every system, bhs_zgesv's `info`)."""
+        with self.lock:
+            self._run(ks, etas, f_hat, out_density, out_matrix, kis, out_info)
+
+    def _run(self, ks, etas, f_hat, out_density, out_matrix, kis, out_info) -> None:
         K = ks.shape[0]
         S = self.batch
+        if out_matrix is None:
+            self._ensure_graphs()
         cur = torch.cuda.current_stream()
         ready = torch.cuda.Event()
         ready.record(cur)
@@ -416,22 +456,13 @@ class SweepEngine:
                     self._assemble(s)
                     out_matrix[i0 : i0 + n].copy_(s.A[:n], non_blocking=True)
                     _ops.zgesv_batched_(s.A, s.rhs, s.bufs)
-                elif not self.use_graphs:
-                    self._body(s)
                 elif s.graph is not None:
                     s.graph.replay()
-                elif not s.warm:
-                    self._body(s)  # first use of the slot: eager run, which also warms every kernel up
-                    s.warm = True
                 else:
-                    # second use (in this or a later sweep): capture the (assembly -> LU) sequence once, then replay
-                    s.stream.synchronize()
-                    g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g, stream=s.stream):
-                        self._body(s)
-                    s.graph = g
-                    g.replay()
+                    self._body(s)
                 out_density[i0 : i0 + n].copy_(s.rhs[:n], non_blocking=True)
+                if out_info is not None:  # padded systems of a partial group are not reported
+                    out_info[i0 : i0 + n].copy_(s.bufs.info[:n], non_blocking=True)
         for s in self.slots:
             done = torch.cuda.Event()
             done.record(s.stream)
@@ -501,13 +532,15 @@ def clear_engines() -> None:
 # --------------------------------------------------------------------------------------------------
 # biem (mirror of _biem.py:453-819)
 # --------------------------------------------------------------------------------------------------
-def _boundary_data(bt, plan, ns, cen, rad, al, be, uin, uin_grad, batch_shape):
+def _boundary_data(spec, plan, ns, cen, rad, al, be, uin, uin_grad, batch_shape):
     """g[K, Q, B] from arbitrary callables (the reference's `f` closure, _biem.py:611-624).
 
     The callables see x of shape (c_ndim, Q, B, *batch) in the caller's namespace -- the reference's
     (c_ndim, ...(f), B, ...(first)) with the quadrature grid flattened -- and return (Q, B, *batch).
+    ``cen`` and the plan's quadrature directions live in the chain frame of the tree; the callables get the points (and
+    the normals) in the caller's cartesian frame.
     """
-    d = len(bt) + 1
+    d = spec.d
     nb = len(batch_shape)
     K = int(np.prod(batch_shape)) if nb else 1
     dirs_np, _ = plan.quadrature()
@@ -520,6 +553,9 @@ def _boundary_data(bt, plan, ns, cen, rad, al, be, uin, uin_grad, batch_shape):
         rad_e.movedim(-1, 0)[None, None] * dirs[(...,) + (None,) * (1 + nb)]
         + cen_e.movedim(-1, 0).movedim(-1, 1)[:, None]
     )  # [d, Q, B, *batch]
+    if not spec.identity:
+        inv = list(spec.inverse)
+        x, dirs = x[inv], dirs[inv]
     xu = ns.out(x.contiguous())
     yhat = ns.out(dirs)[(...,) + (None,) * (1 + nb)]  # [d, Q, 1, *1]
 
@@ -565,10 +601,12 @@ def biem(
     ``translational_coefficients_method`` is accepted for signature compatibility; the B200 path always uses the
     per-entry-exact sparse coupling sum (no `triplet` quadrature noise).
     """
-    bt = branching_types_of(c)
-    d = len(bt) + 1
+    spec = tree_spec(c)
+    d = spec.d
     ns = _NS(centers, radii, k, eta)
-    cen, rad, kk, et, al, be = _check_biem_inputs(bt, centers, radii, k, eta, alpha, beta)
+    cen_user, rad, kk, et, al, be = _check_biem_inputs(d, centers, radii, k, eta, alpha, beta)
+    # the device code works in the chain frame of the tree (b' / relabelled trees: a permutation of the cartesian axes)
+    cen = cen_user if spec.identity else cen_user[..., list(spec.axes)].contiguous()
     del translational_coefficients_method
     nb = kk.dim()
     batch_shape = tuple(torch.broadcast_shapes(kk.shape, et.shape, cen.shape[:-2], rad.shape[:-1], al.shape[:-1], be.shape[:-1]))
@@ -618,13 +656,13 @@ def biem(
             kin = kin.expand(batch_shape).reshape(K).contiguous() if nb else kin.reshape(1)
             if kin_im is not None:
                 kin_im = kin_im.expand(batch_shape).reshape(K).contiguous() if nb else kin_im.reshape(1)
-            dirv = _t(tag["direction"], F64).reshape(d).contiguous()
+            dirv = _t(tag["direction"], F64).reshape(d)[list(spec.axes)].contiguous()
             f_hat = _ops.rhs_expand(d, n_end, centers=c0, radii=r0, k_in=kin, direction=dirv,
                                     alpha=a0 if uin is not None else torch.zeros_like(a0),
-                                    beta=b0 if uin_grad is not None else None, k_in_im=kin_im)
+                                    beta=b0 if uin_grad is not None else None, k_in_im=kin_im, tree=spec.tree)
         else:
-            g = _boundary_data(bt, plan, ns, cen, rad, al, be, uin, uin_grad, batch_shape)
-            f_hat = _ops.rhs_expand(d, n_end, g=g)  # [K, B, H]
+            g = _boundary_data(spec, get_plan(d, n_end, spec.tree), ns, cen, rad, al, be, uin, uin_grad, batch_shape)
+            f_hat = _ops.rhs_expand(d, n_end, g=g, tree=spec.tree)  # [K, B, H]
 
     use_matrix = (uin is None and uin_grad is None) or B > 1 or force_matrix
 
@@ -657,19 +695,32 @@ def biem(
         else:
             density_t = torch.empty((K, N), dtype=C128, device=_dev())
             matrix_t = torch.empty((K, N, N), dtype=C128, device=_dev()) if keep_matrix else None
+            info_t = torch.zeros((K,), dtype=torch.int32, device=_dev())
             rhs = f_hat.reshape(K, N)
             if shared_geom:
                 batch, nslots = _sweep_shape(N, K)
                 eng = _get_engine(d, n_end, B, nslots, complex_k=kis is not None, batch=batch)
                 eng.set_geometry(*geom(0))
-                eng.run(ks, ets, rhs, density_t, matrix_t, kis=kis)
+                eng.run(ks, ets, rhs, density_t, matrix_t, kis=kis, out_info=info_t)
             else:
                 eng = _get_engine(d, n_end, B, 1, complex_k=kis is not None)
                 for i in range(K):
                     eng.set_geometry(*geom(i))
                     eng.run(ks[i : i + 1], ets[i : i + 1], rhs[i : i + 1], density_t[i : i + 1],
                             None if matrix_t is None else matrix_t[i : i + 1],
-                            kis=None if kis is None else kis[i : i + 1])
+                            kis=None if kis is None else kis[i : i + 1], out_info=info_t[i : i + 1])
+            # Exactly singular systems (zero pivot, bhs_zgesv `info` != 0): the reference's solve raises LinAlgError.  NumPy
+            # callers get the same (their results are copied to the host anyway); for torch callers the check stays on the
+            # device -- the densities of the singular systems become NaN, so they cannot be mistaken for solutions, and a
+            # sweep is never synchronised with the host.
+            if ns.kind == "numpy":
+                bad = torch.nonzero(info_t).reshape(-1)
+                if bad.numel():
+                    i_bad = int(bad[0])
+                    raise np.linalg.LinAlgError(
+                        f"Singular matrix: zero pivot at step {int(info_t[i_bad]) - 1} of system {i_bad} (k = {complex(ks[i_bad]) if kis is None else complex(ks[i_bad], kis[i_bad])})")
+            else:
+                density_t = torch.where((info_t != 0)[:, None], torch.full_like(density_t, float("nan")), density_t)
 
     # ---- packaging (user namespace) ---------------------------------------------------------------
     density = None if density_t is None else ns.out(density_t.reshape(batch_shape + (B, H)))
@@ -685,16 +736,18 @@ def biem(
                 x = x[(...,) + (None,) * ndim_first]
             return uin(x)
 
-    cen_store = ns.out(torch.movedim(cen, -1, 0))  # [v, ..., B]  (_biem.py:588)
+    cen_store = ns.out(torch.movedim(cen_user, -1, 0))  # [v, ..., B]  (_biem.py:588)
     dev_state = {
-        "bt": bt, "batch_shape": batch_shape, "K": K, "B": B, "ks": ks, "etas": ets,
+        "bt": spec.chain, "batch_shape": batch_shape, "K": K, "B": B, "ks": ks, "etas": ets,
         "ks_host": ks.tolist() if kis is None else torch.complex(ks, kis).tolist(), "etas_host": ets.tolist(),
         "cen": cen, "rad": rad, "density": density_t, "geom_shared": shared_geom,
     }
-    return BIEMResultCalculator(
+    res = BIEMResultCalculator(
         c=c, centers=cen_store, radii=ns.out(rad), k=ns.out(k_user), n_end=n_end, eta=ns.out(et), kind=kind,
-        uin=uin_wrapped, density=density, matrix=matrix, dev_state=dev_state,
+        uin=uin_wrapped, density=density, matrix=matrix,
     )
+    object.__setattr__(res, "_dev_state", dev_state)
+    return res
 
 
 # --------------------------------------------------------------------------------------------------
@@ -707,14 +760,16 @@ def biem_u(res: Any, x: Array, /, far_field: bool = False, per_ball: bool = Fals
         raise ValueError("The BIEMResult does not have density.")
     if res.kind not in ("outer", "inner"):
         raise ValueError(f"Invalid kind: {res.kind}")
-    bt = branching_types_of(res.c)
-    d = len(bt) + 1
+    spec = tree_spec(res.c)
+    d = spec.d
     ns = _NS(x, res.centers, res.radii, res.k, res.eta)
     st = getattr(res, "_dev_state", None) or {}
     if not st:
         # a result record built by hand (or by another implementation): move its fields to the device
         kk, kk_im = _split_k(_t(res.k))
         cen = torch.movedim(_t(res.centers, F64), 0, -1)
+        if not spec.identity:
+            cen = cen[..., list(spec.axes)]  # chain frame
         rad = _t(res.radii, F64)
         et = _t(res.eta, F64)
         dens = _t(res.density, C128)
@@ -738,7 +793,7 @@ def biem_u(res: Any, x: Array, /, far_field: bool = False, per_ball: bool = Fals
     cen_k = cen.expand(batch_shape + (B, d)).reshape(K, B, d) if nb else cen.reshape(1, B, d)
     rad_k = rad.expand(batch_shape + (B,)).reshape(K, B) if nb else rad.reshape(1, B)
 
-    xs = torch.stack([_t(x[i], F64) for i in range(d)], dim=0)
+    xs = torch.stack([_t(x[spec.axes[i]], F64) for i in range(d)], dim=0)  # chain frame
     if expand_x or nb == 0:
         xshape = tuple(xs.shape[1:])
         xf = xs.reshape(d, -1).contiguous()

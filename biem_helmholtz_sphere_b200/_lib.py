@@ -21,6 +21,7 @@ SIGNATURES = {
     "bhs_version": (i32, []),
     "bhs_device_sm_count": (i32, [C.POINTER(i32)]),
     "bhs_plan_create": (i32, [i32, i32, C.POINTER(vp)]),
+    "bhs_plan_create_tree": (i32, [i32, i32, i32, C.POINTER(vp)]),
     "bhs_plan_destroy": (None, [vp]),
     "bhs_plan_harm": (i32, [vp]),
     "bhs_plan_harm2": (i32, [vp]),
@@ -55,6 +56,7 @@ SIGNATURES = {
 KIND_J, KIND_Y, KIND_H1 = 0, 1, 2
 PROF_CATEGORIES = ("lu_gemm", "lu_panel", "lu_trsm", "lu_pack", "lu_rhs", "asm_main", "asm_pre", "uscat", "rhs_expand", "lu_gemm_inner")
 FLAG_PER_BALL, FLAG_FAR_FIELD, FLAG_INNER = 1, 2, 4
+TREE_CHAIN, TREE_HOPF = 0, 1
 
 
 class BhsError(RuntimeError):
@@ -106,13 +108,14 @@ def stream_ptr():
 
 
 class Plan:
-    """Owner of a bhs_plan_t* for (d, n_end) on the current device."""
+    """Owner of a bhs_plan_t* for (d, n_end[, tree]) on the current device."""
 
-    def __init__(self, d: int, n_end: int):
+    def __init__(self, d: int, n_end: int, tree: int = TREE_CHAIN):
         lib = load()
         h = vp()
-        check(lib.bhs_plan_create(d, n_end, C.byref(h)), "bhs_plan_create")
+        check(lib.bhs_plan_create_tree(d, n_end, tree, C.byref(h)), "bhs_plan_create_tree")
         self.handle = h
+        self.tree = tree
         self.d = d
         self.n_end = n_end
         self.H = lib.bhs_plan_harm(h)
@@ -148,16 +151,16 @@ _plans: dict = {}
 _MAX_PLANS = 48
 
 
-def get_plan(d: int, n_end: int) -> Plan:
+def get_plan(d: int, n_end: int, tree: int = TREE_CHAIN) -> Plan:
     import torch
 
-    key = (torch.cuda.current_device(), d, n_end)
+    key = (torch.cuda.current_device(), d, n_end) if tree == TREE_CHAIN else (torch.cuda.current_device(), d, n_end, tree)
     p = _plans.get(key)
     if p is None:
         # plans own device tables (coupling coefficients: ~300 MB at 3-D n_end = 39): keep the most recent _MAX_PLANS
         while len(_plans) >= _MAX_PLANS:
             _plans.pop(next(iter(_plans)))
-        p = Plan(d, n_end)
+        p = Plan(d, n_end, tree)
         _plans[key] = p
     else:
         _plans[key] = _plans.pop(key)

@@ -66,9 +66,10 @@ def harmonics(d: int, n_end: int, xyz, double_band: bool = False) -> torch.Tenso
 
 
 def rhs_expand(d: int, n_end: int, *, g=None, centers=None, radii=None, k_in=None, direction=None, alpha=None,
-               beta=None, B: int | None = None, k_in_im=None) -> torch.Tensor:
-    """f_hat [nsys, B, H]; either sampled boundary data g [nsys, Q, B] or a fused plane wave exp(i (k_in + i k_in_im) d.x)."""
-    plan = get_plan(d, n_end)
+               beta=None, B: int | None = None, k_in_im=None, tree: int = 0) -> torch.Tensor:
+    """f_hat [nsys, B, H]; either sampled boundary data g [nsys, Q, B] or a fused plane wave exp(i (k_in + i k_in_im) d.x).
+    ``tree``: whose quadrature samples the sphere (_lib.TREE_CHAIN, or _lib.TREE_HOPF for the 'caa' tree)."""
+    plan = get_plan(d, n_end, tree)
     if g is not None:
         gt = _c128(g)
         nsys, Q, B = gt.shape

@@ -481,6 +481,7 @@ static int assemble_impl(const bhs_plan_t* plan, int B, int nsys, const double* 
                          const double* d_beta, int b_lo, int b_hi, double* d_A, int64_t ld, int64_t sys_stride, void* d_work,
                          void* stream) {
     if (!plan || B <= 0 || nsys <= 0 || !d_centers || !d_radii || !d_k || !d_A || !d_work) return BHS_ERR_INVALID;
+    if (plan->tree != BHS_TREE_CHAIN) return BHS_ERR_INVALID;  // right-hand-side-only plan (no coupling table)
     if (b_lo < 0 || b_hi > B || b_lo >= b_hi) return BHS_ERR_INVALID;
     const int64_t N = (int64_t)B * plan->H;
     if (ld < N) return BHS_ERR_INVALID;

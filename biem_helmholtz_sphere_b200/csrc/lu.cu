@@ -12,6 +12,8 @@
 //   pipeline stage is two 1-D TMA bulk copies (cp.async.bulk + mbarrier), 3 stages deep.
 #include <cstdlib>
 
+#include <cuda.h>  // CUtensorMap types only; the encoder is fetched with cudaGetDriverEntryPoint
+
 #include "common.cuh"
 #include "prof.h"
 
@@ -146,6 +148,191 @@ __global__ void __launch_bounds__(G_THREADS, 2) zgemm_sub_kernel(GemmArgs g) {
 }
 
 static const size_t G_SMEM = (size_t)G_STAGES * (G_A_STAGE + G_B_STAGE) * sizeof(double);
+
+// =====================================================================================================
+// GEMM, operands straight from the row-major matrices:  C[rows, cols] -= L[rows, k0 .. k0+K) * U[k0 .. k0+K, cols]
+// =====================================================================================================
+// No packed operand images: both operands are fetched by 2-D tensor-map TMA (cp.async.bulk.tensor, SASS UTMALDG) from the
+// row-major complex matrices, 8 complex k per pipeline stage, 128-byte swizzle:
+//   L tile  : box {16 doubles, 64 rows}            -> smem [64 rows][128 B]           (8 KB)
+//   U tile  : 8 boxes {16 doubles, 8 k-rows}, one per group of 8 columns -> smem [8 groups][8 k][128 B]   (8 KB)
+// The real embedding of the complex product is formed in REGISTERS.  One mma.m8n8k4 step contracts the four reals
+// (re, im) of the complex k-indices q and q + 4 of the stage (the pairing that keeps every fragment load free of bank
+// conflicts under the 128-byte swizzle).  Output columns are split by part: one 8x8 tile holds the REAL parts of 8
+// consecutive complex columns, its twin the IMAGINARY parts,
+//   re-tile:  [ar, -ai] . [br, bi]      im-tile:  [ar, ai] . [bi, br]
+// so the B fragments of both are the two halves of ONE 16-byte shared-memory load, the A fragment of the re-tile is the
+// im-tile's with the sign of the odd lanes flipped, and every thread ends up with complete complex numbers (two adjacent
+// columns per 8x8 pair): 32-byte contiguous C accesses.  Accumulators hold -C (negated on load and store), so that the
+// tensor cores only ever add.
+#define T_STAGES 4
+#define T_STAGE_BYTES 8192  // per operand
+struct TmaGemmArgs {
+    cplx* C;
+    int64_t ldc;
+    int64_t row_base, col_base;  // global row / col of tile (0, 0): C indices and TMA coordinates (rows of L, columns of U)
+    int rt0, ct0;                // first row / col tile of this launch
+    int64_t row_lo, row_hi, col_lo, col_hi;  // output window (half open)
+    int64_t sC;                  // per-system stride of C (blockIdx.z)
+    int k0, nks;                 // first k (column of L = row of U) and number of 8-wide stages
+};
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, int x, int y, int z, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+        : "memory");
+}
+
+__device__ __forceinline__ double flip_sign_if(double v, unsigned mask_hi) {
+    return __hiloint2double(__double2hiint(v) ^ (int)mask_hi, __double2loint(v));
+}
+
+__global__ void __launch_bounds__(G_THREADS, 2)
+    zgemm_tma_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__ CUtensorMap mapU, TmaGemmArgs g) {
+    extern __shared__ unsigned char smem_dyn[];
+    __shared__ __align__(8) uint64_t full[T_STAGES];
+    // 1024-byte alignment: the 128-byte swizzle pattern is a function of the shared-memory address bits 7..9
+    unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    unsigned char* smA = smem;
+    unsigned char* smB = smem + T_STAGES * T_STAGE_BYTES;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 1, wn = warp & 1;
+    const int rt = g.rt0 + blockIdx.y, ct = g.ct0 + blockIdx.x;
+    const int z = blockIdx.z;
+    g.C += (int64_t)z * g.sC;
+    const int trow = (int)(g.row_base + (int64_t)rt * G_TM);  // TMA coordinates of the tile
+    const int tcol = (int)(g.col_base + (int64_t)ct * G_TN);
+    // The nine box loads of a stage are issued by the four warps' first lanes (warp w: operand boxes 3w .. 3w+2 of
+    // {L, U group 0, .., U group 7}), so that no single warp carries the whole issue cost of a stage; the barrier's
+    // expected byte count is posted by warp 0 (complete_tx of the other warps' loads may arrive first: the phase cannot
+    // complete before its one pending arrival).
+    auto issue = [&](int it, int s, int part) {
+        const int kk = g.k0 + it * G_KC;
+        if (part == 0) mbar_expect_tx(&full[s], 2 * T_STAGE_BYTES);
+        const int b0 = part < 0 ? 0 : (part == 0 ? 0 : 3 * part - 1), b1 = part < 0 ? 9 : (part == 3 ? 9 : 3 * part + 2);
+        for (int b = b0; b < b1; ++b) {
+            if (b == 0)
+                tma_load_3d(smA + s * T_STAGE_BYTES, &mapL, 2 * kk, trow, z, &full[s]);
+            else
+                tma_load_3d(smB + s * T_STAGE_BYTES + (b - 1) * 1024, &mapU, 2 * (tcol + 8 * (b - 1)), kk, z, &full[s]);
+        }
+    };
+    if (tid == 0) {
+        for (int s = 0; s < T_STAGES; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (lane == 0)
+        for (int s = 0; s < T_STAGES && s < g.nks; ++s) issue(s, s, warp);
+    // accumulators <- -C : acc_re / acc_im [row block i][column block j][2 adjacent columns]
+    double are[4][4][2], aim[4][4][2];
+    const int64_t row0 = g.row_base + (int64_t)rt * G_TM + wm * 32 + (lane >> 2);
+    const int64_t col0 = g.col_base + (int64_t)ct * G_TN + wn * 32 + 2 * (lane & 3);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t r = row0 + 8 * i;
+        const bool rv = r >= g.row_lo && r < g.row_hi;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int64_t c = col0 + 8 * j + e;
+                cplx v = cmake(0.0, 0.0);
+                if (rv && c >= g.col_lo && c < g.col_hi) v = g.C[r * g.ldc + c];
+                are[i][j][e] = -v.x;
+                aim[i][j][e] = -v.y;
+            }
+        }
+    }
+    const unsigned odd_sign = (lane & 1) ? 0x80000000u : 0u;
+    const bool odd = lane & 1;
+    const int kx = (lane & 2) ? 4 : 0, rx = lane >> 2;
+    const int a_base = (wm * 32 + rx) * 128 + (lane & 1) * 8;
+    const int b_base = wn * 4 * 1024;
+    for (int it = 0; it < g.nks; ++it) {
+        const int s = it % T_STAGES;
+        mbar_wait(&full[s], (it / T_STAGES) & 1);
+        const unsigned char* As = smA + s * T_STAGE_BYTES + a_base;
+        const unsigned char* Bs = smB + s * T_STAGE_BYTES + b_base;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int k = q + kx;  // complex k index of this lane inside the stage
+            double ap[4], ac[4], bre[4], bim[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                ap[i] = *reinterpret_cast<const double*>(As + i * 1024 + ((k ^ rx) << 4));
+                ac[i] = flip_sign_if(ap[i], odd_sign);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double2 v = *reinterpret_cast<const double2*>(Bs + j * 1024 + k * 128 + ((rx ^ k) << 4));
+                bre[j] = odd ? v.y : v.x;
+                bim[j] = odd ? v.x : v.y;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    dmma884(are[i][j][0], are[i][j][1], ac[i], bre[j]);
+                    dmma884(aim[i][j][0], aim[i][j][1], ap[i], bim[j]);
+                }
+        }
+        __syncthreads();
+        if (lane == 0 && it + T_STAGES < g.nks) {
+            fence_proxy_async();
+            issue(it + T_STAGES, s, warp);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t r = row0 + 8 * i;
+        const bool rv = r >= g.row_lo && r < g.row_hi;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int64_t c = col0 + 8 * j + e;
+                if (rv && c >= g.col_lo && c < g.col_hi) g.C[r * g.ldc + c] = cmake(-are[i][j][e], -aim[i][j][e]);
+            }
+        }
+    }
+}
+static const size_t T_SMEM = (size_t)T_STAGES * 2 * T_STAGE_BYTES + 1024;
+
+// ---- tensor maps (driver entry point fetched through the runtime: no link-time dependency on libcuda) -----------------
+typedef CUresult (*bhs_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static bhs_encode_tiled_fn get_encode_tiled() {
+    static bhs_encode_tiled_fn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return (bhs_encode_tiled_fn)f;
+    }();
+    return fn;
+}
+// View of `nbatch` row-major complex matrices [nrows, ncols] (leading dimension ld, `stride` complex elements apart) as a
+// rank-3 tensor of doubles {2 ncols, nrows, nbatch}; box = {16 doubles, box_rows, 1}, 128-byte swizzle, zero fill outside.
+static int make_operand_map(CUtensorMap* m, const void* base, int64_t nrows, int64_t ncols, int64_t ld, int nbatch,
+                            int64_t stride, int box_rows) {
+    bhs_encode_tiled_fn enc = get_encode_tiled();
+    if (!enc) return BHS_ERR_UNSUPPORTED;
+    if (((uintptr_t)base & 15) != 0) return BHS_ERR_INVALID;
+    cuuint64_t dims[3] = {(cuuint64_t)(2 * ncols), (cuuint64_t)nrows, (cuuint64_t)nbatch};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 16, (cuuint64_t)(nbatch > 1 ? stride : ld * nrows) * 16};
+    cuuint32_t box[3] = {16, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? BHS_OK : BHS_ERR_INVALID;
+}
+
 
 // ---- packing -------------------------------------------------------------------------------------------
 // Lp tile (rt, stage): [64 rows][20] doubles, row r = interleaved complex A[row_base + 64 rt + r][k0 + 8 stage ..]
@@ -505,6 +692,213 @@ __global__ void __launch_bounds__(LU_R) lu_select_unrolled_kernel(const cplx* __
     if (is_final) select_finish(fin, w, s_win, tid);
 }
 
+// =====================================================================================================
+// Cluster-resident panel: partial pivoting over up to 4096 rows in ONE launch
+// =====================================================================================================
+// A thread-block cluster of up to 16 CTAs holds 256 candidate rows each (two lanes per row, 16 columns per lane, in
+// registers) and eliminates them with ordinary partial pivoting: per pivot column every CTA finds its best row (warp
+// reductions + one block barrier, as in lu_select_kernel), pushes {key, 1/pivot, pivot row} into a slot of EVERY CTA of the
+// cluster with st.async (distributed shared memory; the bytes complete a transaction barrier in the receiving CTA, so there is
+// no cluster-wide barrier in the loop), and after its own barrier has collected the cluster's candidates each CTA picks the
+// same winner and updates its rows.  Slots and barriers are double buffered by step parity: a CTA can only send step c + 2
+// after it has received every CTA's step c + 1, which they send after their last read of step c.
+// Measured cost of one exchange (tools/cluster_probe.cu, B200): 2 / 4 / 8 / 16 CTAs: ~1.0 / 1.2 / 1.5 / 2.4 k cycles.
+//
+// When the cluster holds ALL rows of the panel (M <= 256 x cluster size) this is the whole panel factorisation: the rows that
+// were never chosen end up holding their multipliers, i.e. L21, which they write back themselves (no lu_l21_kernel, no
+// tournament rounds: 1 launch instead of 5).  Larger panels (C5: 36 864 rows) first run tournament rounds of
+// lu_select_kernel until at most 4096 candidates are left; the cluster then plays the final.
+#define CP_ROWS 256
+#define CP_Q 2
+#define CP_THREADS (CP_ROWS * CP_Q)
+#define CP_NW (CP_THREADS / 32)
+#define CP_LC (LU_NB / CP_Q)
+#define CP_MAXC 16
+#define CP_SLOT_CHUNKS (2 + LU_NB)  // 16-byte chunks of a slot: {key, row}, 1/pivot, 32 row entries
+struct __align__(16) CpSlot {
+    unsigned long long key;
+    int32_t row;
+    int32_t pad;
+    cplx rinv;
+    cplx prow[LU_NB];
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_async_16(uint32_t dst, unsigned long long v0, unsigned long long v1, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];" ::"r"(dst), "l"(v0),
+                 "l"(v1), "r"(remote_bar)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+__global__ void __launch_bounds__(CP_THREADS, 1)
+    lu_panel_cluster_kernel(cplx* __restrict__ A, int64_t ld, int64_t col0, int w, const int32_t* __restrict__ rows_in, int64_t n_in,
+                            int64_t row_begin, int64_t row_end, SelectFinal fin, int write_l21, LuBatch bs) {
+    A += (int64_t)blockIdx.z * bs.sA;
+    if (rows_in) rows_in += (int64_t)blockIdx.z * bs.sCand;
+    fin.ipiv += (int64_t)blockIdx.z * bs.sIpiv;
+    fin.info += blockIdx.z;
+    fin.dblk += (int64_t)blockIdx.z * bs.sDblk;
+    __shared__ cplx prow[2][CP_NW][LU_NB];
+    __shared__ cplx prinv[2][CP_NW];
+    __shared__ unsigned long long wkey[2][CP_NW];
+    __shared__ int32_t wrow[2][CP_NW];
+    __shared__ CpSlot cslot[2][CP_MAXC];
+    __shared__ __align__(8) uint64_t cbar[2];
+    __shared__ int32_t s_win[LU_NB];
+    const uint32_t rank = cluster_ctarank(), csz = cluster_nctarank();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane & (CP_Q - 1), pair = lane / CP_Q;
+    if (tid == 0) {
+        mbar_init(&cbar[0], 1);
+        mbar_init(&cbar[1], 1);
+        mbar_fence_init();
+    }
+    if (tid < LU_NB) s_win[tid] = -1;
+    // which global row does this pair of lanes own?
+    const int64_t slot = (int64_t)rank * CP_ROWS + warp * (32 / CP_Q) + pair;
+    int32_t myrow = -1;
+    if (rows_in) {
+        if (slot < n_in) myrow = rows_in[slot];
+    } else {
+        const int64_t r = row_begin + slot;
+        if (r < row_end) myrow = (int32_t)r;
+    }
+    cplx x[CP_LC];
+    {
+        const cplx* src = A + (int64_t)(myrow >= 0 ? myrow : 0) * ld + col0 + g;
+#pragma unroll
+        for (int i = 0; i < CP_LC; ++i) x[i] = (myrow >= 0 && CP_Q * i + g < w) ? __ldg(src + CP_Q * i) : cmake(0.0, 0.0);
+    }
+    bool active = myrow >= 0;
+    __syncthreads();
+    if (csz > 1) cluster_sync_all();  // every CTA's barriers are initialised before anybody sends
+    const int ncb = (w + CP_Q - 1) / CP_Q;
+#pragma unroll 1
+    for (int cb = 0; cb < ncb; ++cb) {
+#pragma unroll
+        for (int gg = 0; gg < CP_Q; ++gg) {
+            const int c = CP_Q * cb + gg;
+            if (c < w) {
+                const int buf = c & 1;
+                const double mag = fabs(x[0].x) + fabs(x[0].y);
+                const unsigned long long key =
+                    (active && g == gg) ? (unsigned long long)__double_as_longlong(mag) + 1ULL : 0ULL;
+                int bl;
+                const unsigned long long wbest = warp_argmax_u64(key, bl);
+                cplx xc;  // this row's entry in the pivot column, for both lanes of the pair
+                xc.x = __shfl_sync(0xffffffffu, x[0].x, (lane & ~(CP_Q - 1)) | gg);
+                xc.y = __shfl_sync(0xffffffffu, x[0].y, (lane & ~(CP_Q - 1)) | gg);
+                if (pair == bl / CP_Q) {
+                    if (lane == bl) {
+                        wkey[buf][warp] = wbest;
+                        wrow[buf][warp] = myrow;
+                        if (wbest) prinv[buf][warp] = wbest > 1ULL ? crecip_fast(x[0]) : cmake(0.0, 0.0);
+                    }
+                    if (wbest) {
+#pragma unroll
+                        for (int i = 0; i < CP_LC; ++i) prow[buf][warp][CP_Q * i + g] = x[i];  // rotated like x
+                    }
+                }
+                __syncthreads();
+                int bw;
+                const unsigned long long ctabest = warp_argmax_u64(wkey[buf][lane & (CP_NW - 1)], bw);
+                unsigned long long best = ctabest;
+                const cplx* pr = prow[buf][bw];
+                cplx rinv = prinv[buf][bw];
+                int32_t winrow = wrow[buf][bw];
+                if (csz > 1) {
+                    if (tid == 0) mbar_expect_tx(&cbar[buf], csz * (uint32_t)sizeof(CpSlot));
+                    const uint32_t my_slot = smem_u32(&cslot[buf][rank]), my_bar = smem_u32(&cbar[buf]);
+                    for (int t = tid; t < CP_SLOT_CHUNKS * (int)csz; t += CP_THREADS) {
+                        const uint32_t peer = t / CP_SLOT_CHUNKS, ch = t % CP_SLOT_CHUNKS;
+                        unsigned long long v0, v1;
+                        if (ch == 0) {
+                            v0 = ctabest;
+                            v1 = (unsigned long long)(uint32_t)winrow;
+                        } else {
+                            const cplx e = ch == 1 ? rinv : pr[ch - 2];
+                            v0 = (unsigned long long)__double_as_longlong(e.x);
+                            v1 = (unsigned long long)__double_as_longlong(e.y);
+                        }
+                        st_async_16(mapa_shared(my_slot + ch * 16, peer), v0, v1, mapa_shared(my_bar, peer));
+                    }
+                    while (!mbar_try_wait(&cbar[buf], (uint32_t)(c >> 1) & 1u)) {
+                    }
+                    int bc;
+                    best = warp_argmax_u64(lane < (int)csz ? cslot[buf][lane].key : 0ULL, bc);  // lowest rank wins a tie
+                    pr = cslot[buf][bc].prow;
+                    rinv = cslot[buf][bc].rinv;
+                    winrow = cslot[buf][bc].row;
+                }
+                const bool any = best != 0ULL;     // at least one active row left
+                const bool nonzero = best > 1ULL;  // its pivot entry is not exactly zero
+                if (tid == 0) {
+                    s_win[c] = any ? winrow : -1;
+                    if (rank == 0 && any && !nonzero) atomicCAS(fin.info, 0, (int)(fin.j + c + 1));
+                }
+                if (any && active && myrow == winrow) {  // the pivot row IS row c of the factored diagonal block
+#pragma unroll
+                    for (int i = 0; i < CP_LC; ++i) fin.dblk[c * LU_NB + CP_Q * ((cb + i) & (CP_LC - 1)) + g] = x[i];
+                    active = false;
+                }
+                if (any && active && nonzero) {
+                    const cplx l = cmul(xc, rinv);
+                    const cplx ml = cmake(-l.x, -l.y);
+                    if (g == gg) x[0] = l;
+                    else if (g > gg) x[0] = cfma(ml, pr[g], x[0]);
+#pragma unroll
+                    for (int i = 1; i < CP_LC; ++i)
+                        if (cb + i < CP_LC) x[i] = cfma(ml, pr[CP_Q * i + g], x[i]);
+                }
+            }
+        }
+        const cplx t = x[0];
+#pragma unroll
+        for (int i = 1; i < CP_LC; ++i) x[i - 1] = x[i];
+        x[CP_LC - 1] = t;
+    }
+    // rows that never pivoted hold their multipliers: that is L21 (only when every row of the panel was a candidate)
+    if (write_l21 && active) {
+        cplx* dst = A + (int64_t)myrow * ld + col0;
+#pragma unroll
+        for (int i = 0; i < CP_LC; ++i) {
+            const int col = CP_Q * ((ncb + i) & (CP_LC - 1)) + g;
+            if (col < w) dst[col] = x[i];
+        }
+    }
+    if (csz > 1) cluster_sync_all();  // nobody leaves while a peer could still be writing into its slots
+    if (rank == 0) {
+        __syncthreads();
+        select_finish(fin, w, s_win, tid);
+    }
+}
+
 // Apply the row interchanges of one panel to the matrix (and, in the same launch, to the right-hand sides) from the
 // panel's NET row map: all the rows of the diagonal block go through a shared-memory tile, so that every global load
 // is independent (the LAPACK-style sequence of 32 swaps is a chain of 32 dependent round trips per column).  64
@@ -664,63 +1058,124 @@ __global__ void __launch_bounds__(256) rhs_gemv_sub_kernel(const cplx* __restric
     }
 }
 // Solve the T x T (T <= 128) diagonal block at k0 against rhs rows [k0, k0+T): lower-unit (forward) or upper (backward).
-// The block is staged in shared memory 64 columns at a time (column-major, so that step q reads one contiguous column),
-// instead of every step fetching a strided column from global memory: 128 dependent L2 latencies become 2 bulk loads.
-#define RS_CH 64
-__global__ void __launch_bounds__(128) rhs_block_solve_kernel(const cplx* __restrict__ M, int64_t ld, int64_t k0, int T,
-                                                              int upper, cplx* __restrict__ rhs, int nrhs, int64_t sA,
-                                                              int64_t sRhs) {
+// The block is consumed in 32-column strips (rows at / below the strip's diagonal sub-block for the lower solve, at / above
+// it for the upper one).  Each strip is staged in shared memory row by row (512 contiguous bytes per row, pitch 33 so that
+// both access patterns below are conflict-free); the loads of the NEXT strip are issued into registers before the current
+// one is used, so that their latency hides behind the arithmetic.  Per strip: the warp that owns the 32 x 32 diagonal
+// sub-block solves it with one row per lane (the solved entries travel by warp shuffle, no block barrier inside the 32
+// steps), then every other row subtracts its 32-term dot product.  Two block barriers per strip and column instead of two
+// per matrix column (54 us -> ~8 us for a 128 x 128 block).
+#define RS_W 32
+#define RS_PITCH (RS_W + 1)
+#define RS_NC 4  // right-hand-side columns handled per pass over the strips
+__global__ void __launch_bounds__(128) rhs_block_solve_kernel(const cplx* __restrict__ M, int64_t ld, int64_t k0, int T, int upper,
+                                                              cplx* __restrict__ rhs, int nrhs, int64_t sA, int64_t sRhs) {
     M += (int64_t)blockIdx.z * sA;
     rhs += (int64_t)blockIdx.z * sRhs;
-    extern __shared__ __align__(16) cplx s_blk[];  // [RS_CH][LU_NBO + 1]
-    __shared__ cplx v[LU_NBO];
-    __shared__ cplx rd[RS_CH];
-    const int tid = threadIdx.x;
-    constexpr int LDB = LU_NBO + 1;
-    for (int c = 0; c < nrhs; ++c) {
-        if (tid < T) v[tid] = rhs[(k0 + tid) * nrhs + c];
-        const int nch = (T + RS_CH - 1) / RS_CH;
-        for (int chi = 0; chi < nch; ++chi) {
-            const int ch = upper ? nch - 1 - chi : chi;
-            const int c0 = ch * RS_CH, cw = min(RS_CH, T - c0);
-            __syncthreads();  // v loaded / previous chunk consumed
-            // stage columns [c0, c0 + cw) of the block: rows are read 64 consecutive elements at a time
-            for (int e = tid; e < T * RS_CH; e += 128) {
-                const int r = e / RS_CH, cc = e % RS_CH;
-                if (cc < cw) s_blk[cc * LDB + r] = M[(k0 + r) * ld + k0 + c0 + cc];
+    extern __shared__ __align__(16) cplx s_strip[];  // [LU_NBO][RS_PITCH]
+    __shared__ cplx v[RS_NC][LU_NBO];
+    __shared__ cplx rdiag[LU_NBO];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nsub = (T + RS_W - 1) / RS_W;
+    M += k0 * ld + k0;
+    if (upper) {
+        cplx dg = cmake(1.0, 0.0);
+        if (tid < T) dg = M[(int64_t)tid * ld + tid];
+        rdiag[tid] = (dg.x != 0.0 || dg.y != 0.0) ? crecip(dg) : cmake(1.0, 0.0);
+    }
+    // strip `si` (in processing order): sub-block index sb, rows [r_lo, r_hi) of the block, columns [32 sb, 32 sb + 32)
+    auto strip_rows = [&](int si, int& sb, int& r_lo, int& r_hi) {
+        sb = upper ? nsub - 1 - si : si;
+        r_lo = upper ? 0 : RS_W * sb;
+        r_hi = upper ? min(T, RS_W * sb + RS_W) : T;
+    };
+    cplx pre[RS_W];  // this thread's share of the next strip: elements e = tid + 128 i  ->  (row r_lo + e / 32, column e % 32)
+    auto prefetch = [&](int si) {
+        int sb, r_lo, r_hi;
+        strip_rows(si, sb, r_lo, r_hi);
+        const int n = (r_hi - r_lo) * RS_W;
+#pragma unroll
+        for (int i = 0; i < RS_W; ++i) {
+            const int e = tid + 128 * i;
+            const int r = r_lo + e / RS_W, cc = RS_W * sb + (e % RS_W);
+            pre[i] = (e < n && cc < T) ? M[(int64_t)r * ld + cc] : cmake(0.0, 0.0);
+        }
+    };
+    for (int c0 = 0; c0 < nrhs; c0 += RS_NC) {
+        const int nc = min(RS_NC, nrhs - c0);
+        __syncthreads();
+        for (int c = 0; c < nc; ++c) v[c][tid] = tid < T ? rhs[(k0 + tid) * nrhs + c0 + c] : cmake(0.0, 0.0);
+        prefetch(0);
+        for (int si = 0; si < nsub; ++si) {
+            int sb, r_lo, r_hi;
+            strip_rows(si, sb, r_lo, r_hi);
+            __syncthreads();  // the previous strip has been consumed
+            {
+                const int n = (r_hi - r_lo) * RS_W;
+#pragma unroll
+                for (int i = 0; i < RS_W; ++i) {
+                    const int e = tid + 128 * i;
+                    if (e < n) s_strip[(e / RS_W) * RS_PITCH + (e % RS_W)] = pre[i];
+                }
             }
+            if (si + 1 < nsub) prefetch(si + 1);
             __syncthreads();
-            if (upper) {
-                if (tid < cw) {
-                    const cplx dg = s_blk[tid * LDB + c0 + tid];
-                    rd[tid] = (dg.x != 0.0 || dg.y != 0.0) ? crecip(dg) : cmake(1.0, 0.0);
+            const int d0 = RS_W * sb;  // first row / column of the diagonal sub-block
+            for (int c = 0; c < nc; ++c) {
+                if (warp == sb) {
+                    // 32 x 32 triangular solve, row d0 + lane per lane
+                    // (rows beyond T of a tail block hold x = 0 and never touch the -- unstaged -- strip rows)
+                    const bool valid = d0 + lane < T;
+                    const cplx* row = s_strip + (valid ? d0 + lane - r_lo : 0) * RS_PITCH;
+                    cplx x = v[c][d0 + lane];
+                    if (upper) {
+#pragma unroll
+                        for (int q = RS_W - 1; q >= 0; --q) {
+                            if (lane == q) x = cmul(x, rdiag[d0 + q]);
+                            cplx xq;
+                            xq.x = __shfl_sync(0xffffffffu, x.x, q);
+                            xq.y = __shfl_sync(0xffffffffu, x.y, q);
+                            const cplx m = row[q];
+                            if (lane < q && valid) x = cfma(cmake(-m.x, -m.y), xq, x);
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < RS_W; ++q) {
+                            cplx xq;
+                            xq.x = __shfl_sync(0xffffffffu, x.x, q);
+                            xq.y = __shfl_sync(0xffffffffu, x.y, q);
+                            const cplx m = row[q];
+                            if (lane > q && valid) x = cfma(cmake(-m.x, -m.y), xq, x);
+                        }
+                    }
+                    v[c][d0 + lane] = x;
                 }
                 __syncthreads();
-                for (int q = c0 + cw - 1; q >= c0; --q) {
-                    if (tid == q) v[q] = cmul(v[q], rd[q - c0]);
-                    __syncthreads();
-                    const cplx xq = v[q], m = s_blk[(q - c0) * LDB + tid];
-                    if (tid < q) v[tid] = cfma(cmake(-m.x, -m.y), xq, v[tid]);
-                    __syncthreads();
+                // the other rows of the strip: v[r] -= sum_q strip[r][q] x[q]
+                const bool mine = upper ? tid < d0 : (tid >= d0 + RS_W && tid < T);
+                if (mine) {
+                    const cplx* row = s_strip + (tid - r_lo) * RS_PITCH;
+                    cplx a0 = v[c][tid], a1 = cmake(0.0, 0.0);
+#pragma unroll
+                    for (int q = 0; q < RS_W; q += 2) {
+                        const cplx m0 = row[q], m1 = row[q + 1];
+                        a0 = cfma(cmake(-m0.x, -m0.y), v[c][d0 + q], a0);
+                        a1 = cfma(cmake(-m1.x, -m1.y), v[c][d0 + q + 1], a1);
+                    }
+                    v[c][tid] = cadd(a0, a1);
                 }
-            } else {
-                for (int q = c0; q < c0 + cw; ++q) {
-                    const cplx xq = v[q], m = s_blk[(q - c0) * LDB + tid];
-                    if (tid > q && tid < T) v[tid] = cfma(cmake(-m.x, -m.y), xq, v[tid]);
-                    __syncthreads();
-                }
+                // (rows written here are read by the next strip's diagonal solve only after the barrier at its top)
             }
         }
         __syncthreads();
-        if (tid < T) rhs[(k0 + tid) * nrhs + c] = v[tid];
-        __syncthreads();
+        for (int c = 0; c < nc; ++c)
+            if (tid < T) rhs[(k0 + tid) * nrhs + c0 + c] = v[c][tid];
     }
 }
-static const size_t RS_SMEM = (size_t)RS_CH * (LU_NBO + 1) * sizeof(cplx);
+static const size_t RS_SMEM = (size_t)LU_NBO * RS_PITCH * sizeof(cplx);
 // permutation from sequential swaps, applied to a few columns (used by the stand-alone zgetrs)
 __global__ void rhs_apply_ipiv_kernel(const int32_t* __restrict__ ipiv, int64_t N, cplx* __restrict__ rhs, int nrhs) {
-    if (blockIdx.x != 0) return;
-    int c = threadIdx.x;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per right-hand-side column, any number of columns
     if (c >= nrhs) return;
     for (int64_t i = 0; i < N; ++i) {
         int64_t p = ipiv[i];
@@ -752,7 +1207,14 @@ struct LuCtx {
     LuBatch bs;
     cudaStream_t st;
     int err;
+    bool tma;           // operands by tensor-map TMA straight from A (default); false = packed operand images (BHS_GEMM_PACKED=1)
+    CUtensorMap mapL, mapU;  // A viewed with the L-operand box {8 complex, 64 rows} and the U-operand box {8 complex, 8 rows}
 };
+
+static bool gemm_packed_requested() {
+    static const bool v = getenv("BHS_GEMM_PACKED") != nullptr;
+    return v;
+}
 
 struct LuWork {
     int32_t* cand0;
@@ -793,6 +1255,24 @@ static LuWork lu_carve(int64_t N, int nbatch, void* base) {
 static void lu_pack_l(LuCtx& x, int64_t r_lo, int64_t r_hi, int64_t k0, int K);
 static void lu_gemm(LuCtx& x, int64_t r_lo, int64_t r_hi, int64_t c_lo, int64_t c_hi, int64_t k0, int K) {
     if (r_lo >= r_hi || c_lo >= c_hi || K <= 0) return;
+    const int pcat = (K >= LU_NBO || (k0 == x.J && r_lo >= x.J + LU_NBO)) ? BHS_PROF_LU_GEMM : BHS_PROF_LU_GEMM_IN;
+    if (x.tma) {
+        TmaGemmArgs t;
+        t.C = x.A; t.ldc = x.ld;
+        t.row_base = x.J; t.col_base = 0;
+        t.rt0 = (int)((r_lo - x.J) / G_TM);
+        t.ct0 = (int)(c_lo / G_TN);
+        const int rt1 = (int)((r_hi - 1 - x.J) / G_TM), ct1 = (int)((c_hi - 1) / G_TN);
+        t.row_lo = r_lo; t.row_hi = r_hi; t.col_lo = c_lo; t.col_hi = c_hi;
+        t.sC = x.bs.sA;
+        t.k0 = (int)k0; t.nks = (K + G_KC - 1) / G_KC;
+        dim3 grid(ct1 - t.ct0 + 1, rt1 - t.rt0 + 1, x.nbatch);
+        bhs_prof_begin(pcat, x.st);
+        zgemm_tma_kernel<<<grid, G_THREADS, T_SMEM, x.st>>>(x.mapL, x.mapU, t);
+        bhs_prof_end(pcat, 8.0 * (double)(r_hi - r_lo) * (double)(c_hi - c_lo) * (double)K * x.nbatch, x.st);
+        LU_LAUNCH_CHECK(x);
+        return;
+    }
     // the L operand is packed here, from the current A: pivoting of later panels of the same outer block
     // permutes rows of earlier L columns, so an image packed at panel time would be stale
     lu_pack_l(x, r_lo, r_hi, k0, K);
@@ -808,7 +1288,6 @@ static void lu_gemm(LuCtx& x, int64_t r_lo, int64_t r_hi, int64_t c_lo, int64_t 
     g.row_lo = r_lo; g.row_hi = r_hi; g.col_lo = c_lo; g.col_hi = c_hi;
     g.sC = x.bs.sA; g.sLp = x.bs.sLp; g.sUp = x.bs.sUp;
     dim3 grid(ct1 - g.ct0 + 1, rt1 - g.rt0 + 1, x.nbatch);
-    const int pcat = (K >= LU_NBO || (k0 == x.J && r_lo >= x.J + LU_NBO)) ? BHS_PROF_LU_GEMM : BHS_PROF_LU_GEMM_IN;
     bhs_prof_begin(pcat, x.st);
     zgemm_sub_kernel<<<grid, G_THREADS, G_SMEM, x.st>>>(g);
     bhs_prof_end(pcat, 8.0 * (double)(r_hi - r_lo) * (double)(c_hi - c_lo) * (double)K * x.nbatch, x.st);
@@ -827,7 +1306,7 @@ static void lu_pack_l(LuCtx& x, int64_t r_lo, int64_t r_hi, int64_t k0, int K) {
     LU_LAUNCH_CHECK(x);
 }
 static void lu_pack_u(LuCtx& x, int64_t k0, int K, int64_t c_lo, int64_t c_hi) {
-    if (c_lo >= c_hi) return;
+    if (c_lo >= c_hi || x.tma) return;
     int64_t c_begin = (c_lo / G_TN) * G_TN, c_end_pad = cdiv64(c_hi, G_TN) * G_TN;
     int Kpad = ((K + G_KC - 1) / G_KC) * G_KC;
     int64_t tot = (c_end_pad - c_begin) * Kpad;
@@ -838,7 +1317,32 @@ static void lu_pack_u(LuCtx& x, int64_t k0, int K, int64_t c_lo, int64_t c_hi) {
     LU_LAUNCH_CHECK(x);
 }
 
-// 32-wide (or narrower) panel at column j: tournament pivoting, swap, diagonal LU, L21
+// Largest cluster the device can schedule for lu_panel_cluster_kernel (16 needs the non-portable attribute), 0 = none.
+// BHS_LU_CLUSTER=0 disables the cluster panel, BHS_LU_CLUSTER=2 also uses it for systems factorised in lock step.
+static int g_cluster_mode = -1, g_cluster_max = 0;
+static void cluster_init() {
+    if (g_cluster_mode >= 0) return;
+    const char* e = getenv("BHS_LU_CLUSTER");
+    g_cluster_mode = e ? atoi(e) : 1;
+    g_cluster_max = 0;
+    if (g_cluster_mode == 0) return;
+    cudaFuncSetAttribute(lu_panel_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    for (int csz = CP_MAXC; csz >= 2 && !g_cluster_max; csz >>= 1) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(csz, 1, 1);
+        cfg.blockDim = dim3(CP_THREADS, 1, 1);
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = csz; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, lu_panel_cluster_kernel, &cfg) == cudaSuccess && n > 0) g_cluster_max = csz;
+    }
+    cudaGetLastError();
+    if (!g_cluster_max) g_cluster_max = 1;  // a "cluster" of one CTA still factors up to 256 rows in one launch
+}
+
+// 32-wide (or narrower) panel at column j: pivot selection, swap, diagonal LU, L21
 static void lu_panel(LuCtx& x, int64_t j, int w) {
     const int64_t M = x.N - j;
     int64_t nsets = cdiv64(M, LU_R);
@@ -846,25 +1350,59 @@ static void lu_panel(LuCtx& x, int64_t j, int w) {
     bhs_prof_begin(BHS_PROF_LU_PANEL, x.st);
     const SelectFinal fin{j, x.ipiv, x.info, x.dblk}, nofin{0, nullptr, nullptr, nullptr};
     const bool quad = x.nbatch == 1;  // 4 lanes per candidate row for a lone system (latency); unrolled one-lane form in a sweep
-    if (quad)
-        lu_select_kernel<4><<<dim3((unsigned)nsets, 1, x.nbatch), LU_R * 4, 0, x.st>>>(x.A, x.ld, j, w, nullptr, 0, j, x.N, x.cand[cur],
-                                                                                   nsets == 1 ? fin : nofin, x.bs);
-    else
-        lu_select_unrolled_kernel<<<dim3((unsigned)nsets, 1, x.nbatch), LU_R, 0, x.st>>>(x.A, x.ld, j, w, nullptr, 0, j, x.N, x.cand[cur],
-                                                                                     nsets == 1 ? fin : nofin, x.bs);
-    LU_LAUNCH_CHECK(x);
-    while (nsets > 1) {
-        int64_t n_in = nsets * LU_NB;
-        int64_t nsets2 = cdiv64(n_in, LU_R);
+    auto select_round = [&](const int32_t* rows_in, int64_t n_in, int64_t ns, int32_t* rows_out, const SelectFinal& f) {
         if (quad)
-            lu_select_kernel<4><<<dim3((unsigned)nsets2, 1, x.nbatch), LU_R * 4, 0, x.st>>>(
-                x.A, x.ld, j, w, x.cand[cur], n_in, 0, 0, x.cand[cur ^ 1], nsets2 == 1 ? fin : nofin, x.bs);
+            lu_select_kernel<4><<<dim3((unsigned)ns, 1, x.nbatch), LU_R * 4, 0, x.st>>>(x.A, x.ld, j, w, rows_in, n_in, j, x.N, rows_out, f, x.bs);
         else
-            lu_select_unrolled_kernel<<<dim3((unsigned)nsets2, 1, x.nbatch), LU_R, 0, x.st>>>(
-                x.A, x.ld, j, w, x.cand[cur], n_in, 0, 0, x.cand[cur ^ 1], nsets2 == 1 ? fin : nofin, x.bs);
+            lu_select_unrolled_kernel<<<dim3((unsigned)ns, 1, x.nbatch), LU_R, 0, x.st>>>(x.A, x.ld, j, w, rows_in, n_in, j, x.N, rows_out, f, x.bs);
         LU_LAUNCH_CHECK(x);
-        cur ^= 1;
-        nsets = nsets2;
+    };
+    cluster_init();
+    bool l21_done = false, done = false;
+    const bool use_cluster = g_cluster_mode && (x.nbatch == 1 || g_cluster_mode >= 2) && M > LU_R;
+    if (use_cluster) {
+        // tournament rounds until one cluster can hold the candidates, then partial pivoting inside the cluster
+        const int64_t cap = (int64_t)g_cluster_max * CP_ROWS;
+        const int32_t* rows_in = nullptr;
+        int64_t n_in = M;
+        while (n_in > cap) {
+            const int64_t ns = cdiv64(n_in, LU_R);
+            select_round(rows_in, n_in, ns, x.cand[cur], nofin);
+            rows_in = x.cand[cur];
+            cur ^= 1;
+            n_in = ns * LU_NB;
+        }
+        const int csz = (int)cdiv64(n_in, CP_ROWS);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(csz, 1, x.nbatch);
+        cfg.blockDim = dim3(CP_THREADS, 1, 1);
+        cfg.stream = x.st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = csz; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        const int direct = rows_in == nullptr;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, lu_panel_cluster_kernel, x.A, x.ld, j, w, rows_in, n_in, j, x.N, fin, direct, x.bs);
+        if (e == cudaSuccess) {
+            BHS_COUNT_LAUNCH();
+            done = true;
+            l21_done = direct;
+        } else {
+            cudaGetLastError();   // this device cannot place the cluster after all: tournament from here on
+            g_cluster_mode = 0;
+            nsets = cdiv64(M, LU_R);
+            cur = 0;
+        }
+    }
+    if (!done) {
+        select_round(nullptr, 0, nsets, x.cand[cur], nsets == 1 ? fin : nofin);
+        while (nsets > 1) {
+            int64_t n_in = nsets * LU_NB;
+            int64_t nsets2 = cdiv64(n_in, LU_R);
+            select_round(x.cand[cur], n_in, nsets2, x.cand[cur ^ 1], nsets2 == 1 ? fin : nofin);
+            cur ^= 1;
+            nsets = nsets2;
+        }
     }
     {
         const int nct = (int)cdiv64(x.N, PERM_COLS), nrt = x.rhs ? (int)cdiv64(x.nrhs, PERM_COLS) : 0;
@@ -872,7 +1410,7 @@ static void lu_panel(LuCtx& x, int64_t j, int w) {
                                                                                       x.bs.sA, x.bs.sRhs, x.bs.sDblk);
         LU_LAUNCH_CHECK(x);
     }
-    if (j + w < x.N) {
+    if (j + w < x.N && !l21_done) {
         lu_l21_kernel<<<dim3((unsigned)cdiv64(x.N - j - w, LU_R), 1, x.nbatch), LU_R, 0, x.st>>>(x.A, x.ld, x.N, j, w, x.bs.sA);
         LU_LAUNCH_CHECK(x);
     }
@@ -913,6 +1451,7 @@ static void lu_rec(LuCtx& x, int64_t j0, int w) {
 static int lu_factor(LuCtx& x) {
     cudaMemsetAsync(x.info, 0, sizeof(int32_t) * x.nbatch, x.st);
     cudaFuncSetAttribute(zgemm_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
+    cudaFuncSetAttribute(zgemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_SMEM);
     cudaFuncSetAttribute(rhs_block_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM);
     // BHS_LU_GEMM_ONLY=1 (measurement aid, wrong results): issue only the trailing updates, to see how much of a
     // sweep's time the DMMA kernel accounts for on its own
@@ -989,6 +1528,12 @@ static int lu_setup(LuCtx& x, int64_t N, double* d_A, int64_t ld, double* d_rhs,
     x.ipiv = d_ipiv; x.info = d_info; x.cand[0] = w.cand0; x.cand[1] = w.cand1; x.dblk = w.dblk;
     x.Lp = w.Lp; x.Up = w.Up; x.nks_total = LU_NBO / G_KC; x.J = 0;
     x.st = (cudaStream_t)stream; x.err = 0;
+    x.tma = !gemm_packed_requested();
+    if (x.tma) {
+        int rc = make_operand_map(&x.mapL, d_A, N, N, ld, nbatch, strideA, G_TM);
+        if (rc == BHS_OK) rc = make_operand_map(&x.mapU, d_A, N, N, ld, nbatch, strideA, G_KC);
+        if (rc != BHS_OK) return rc;
+    }
     return BHS_OK;
 }
 
@@ -1034,7 +1579,7 @@ extern "C" int bhs_zgetrs(int64_t N, int nrhs, const double* d_LU, int64_t ld, c
     x.bs = LuBatch{0, 0, 0, 0, 0, 0, 0};
     x.st = (cudaStream_t)stream; x.err = 0;
     cudaFuncSetAttribute(rhs_block_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM);
-    rhs_apply_ipiv_kernel<<<1, 32, 0, x.st>>>(d_ipiv, N, x.rhs, nrhs);
+    rhs_apply_ipiv_kernel<<<(unsigned)cdiv64(nrhs, 32), 32, 0, x.st>>>(d_ipiv, N, x.rhs, nrhs);
     LU_LAUNCH_CHECK(x);
     for (int64_t J = 0; J < N; J += LU_NBO) {
         int w = (int)((N - J < LU_NBO) ? (N - J) : LU_NBO);
@@ -1061,6 +1606,21 @@ extern "C" int bhs_zgemm_sub(int64_t M, int64_t N, int64_t K, const double* d_A,
         return BHS_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     int64_t nks = cdiv64(K, G_KC);
+    if (!gemm_packed_requested()) {
+        // operands by TMA straight from the caller's matrices (columns of A / rows of B beyond K are zero filled)
+        CUtensorMap mL, mU;
+        int rc = make_operand_map(&mL, d_A, M, K, lda, 1, 0, G_TM);
+        if (rc == BHS_OK) rc = make_operand_map(&mU, d_B, K, N, ldb, 1, 0, G_KC);
+        if (rc != BHS_OK) return rc;
+        cudaFuncSetAttribute(zgemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_SMEM);
+        TmaGemmArgs t;
+        t.C = (cplx*)d_C; t.ldc = ldc; t.row_base = 0; t.col_base = 0; t.rt0 = 0; t.ct0 = 0;
+        t.row_lo = 0; t.row_hi = M; t.col_lo = 0; t.col_hi = N; t.sC = 0; t.k0 = 0; t.nks = (int)nks;
+        dim3 grid((unsigned)cdiv64(N, G_TN), (unsigned)cdiv64(M, G_TM));
+        zgemm_tma_kernel<<<grid, G_THREADS, T_SMEM, st>>>(mL, mU, t);
+        BHS_CHECK_LAUNCH();
+        return BHS_OK;
+    }
     int Kpad = (int)(nks * G_KC);
     double* Lp = (double*)d_work;
     double* Up = (double*)((unsigned char*)d_work + al256(cdiv64(M, G_TM) * nks * G_A_STAGE * 8));

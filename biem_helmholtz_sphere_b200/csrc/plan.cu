@@ -387,13 +387,22 @@ static int build_coupling(bhs_plan* p) {
     return BHS_OK;
 }
 
-extern "C" int bhs_plan_create(int d, int n_end, bhs_plan_t** out) {
+extern "C" int bhs_plan_create(int d, int n_end, bhs_plan_t** out) { return bhs_plan_create_tree(d, n_end, BHS_TREE_CHAIN, out); }
+
+// tree = BHS_TREE_HOPF: the harmonic SPACE (degree < n_end on S^3) and its chain basis are those of the 'bba' plan -- the
+// tree only changes where the right-hand-side quadrature samples the sphere (type-c root: n_end Gauss-Legendre nodes in
+// cos 2 theta_0, 2 n_end equispaced nodes on each of the two type-a circles), which is what the reference's `caa` rows pin.
+// Such a plan serves bhs_rhs_expand / bhs_plan_quadrature only (no coupling table).
+extern "C" int bhs_plan_create_tree(int d, int n_end, int tree, bhs_plan_t** out) {
     if (!out) return BHS_ERR_INVALID;
     *out = nullptr;
     if (d < 2 || n_end < 1) return BHS_ERR_INVALID;
+    if (tree != BHS_TREE_CHAIN && tree != BHS_TREE_HOPF) return BHS_ERR_INVALID;
+    if (tree == BHS_TREE_HOPF && d != 4) return BHS_ERR_UNSUPPORTED;
     if (d - 2 > BHS_MAX_NODES) return BHS_ERR_UNSUPPORTED;  // chain types a, ba, bba, bbba, ... up to d = 8
     bhs_plan* p = new (std::nothrow) bhs_plan();
     if (!p) return BHS_ERR_ALLOC;
+    p->tree = tree;
     p->d = d;
     p->s_ndim = d - 1;
     p->n_end = n_end;
@@ -433,6 +442,39 @@ extern "C" int bhs_plan_create(int d, int n_end, bhs_plan_t** out) {
         bhs_plan_destroy(p);
         return rc;
     }
+    if (tree == BHS_TREE_HOPF) {
+        // y = (cos t0 cos t1, cos t0 sin t1, sin t0 cos t2, sin t0 sin t2), t0 in [0, pi/2]; the surface measure is
+        // sin t0 cos t0 dt0 dt1 dt2 = (1/4) d(cos 2 t0) dt1 dt2
+        std::vector<ld> xs, ws;
+        gauss_gegenbauer(n_end, 1, xs, ws);  // Gauss-Legendre
+        const int na = 2 * n_end, Q = n_end * na * na;
+        p->Q = Q;
+        p->h_qdirs.assign((size_t)d * Q, 0.0);
+        p->h_qw.assign(Q, 0.0);
+        for (int i0 = 0; i0 < n_end; ++i0) {
+            const ld t0 = 0.5L * acosl(xs[i0]), c0 = cosl(t0), s0 = sinl(t0);
+            for (int i1 = 0; i1 < na; ++i1) {
+                const ld t1 = 2.0L * PI_L * i1 / na;
+                for (int i2 = 0; i2 < na; ++i2) {
+                    const ld t2 = 2.0L * PI_L * i2 / na;
+                    const int q = (i0 * na + i1) * na + i2;
+                    p->h_qdirs[(size_t)0 * Q + q] = (double)(c0 * cosl(t1));
+                    p->h_qdirs[(size_t)1 * Q + q] = (double)(c0 * sinl(t1));
+                    p->h_qdirs[(size_t)2 * Q + q] = (double)(s0 * cosl(t2));
+                    p->h_qdirs[(size_t)3 * Q + q] = (double)(s0 * sinl(t2));
+                    p->h_qw[q] = (double)(0.25L * ws[i0] * (PI_L / n_end) * (PI_L / n_end));
+                }
+            }
+        }
+        if ((rc = upload(&p->d_qdirs, p->h_qdirs)) || (rc = upload(&p->d_qw, p->h_qw))) {
+            bhs_plan_destroy(p);
+            return rc;
+        }
+        if (cudaMalloc((void**)&p->d_WY, (size_t)Q * p->H * sizeof(cplx)) != cudaSuccess) {
+            bhs_plan_destroy(p);
+            return BHS_ERR_ALLOC;
+        }
+    } else
     // RHS quadrature: product rule, n_end nodes per b-node, 2 n_end on the periodic node
     {
         std::vector<std::vector<ld>> ax(p->s_ndim), aw(p->s_ndim);
@@ -499,7 +541,7 @@ extern "C" int bhs_plan_create(int d, int n_end, bhs_plan_t** out) {
             return rc;
         }
     }
-    if ((rc = build_coupling(p))) {
+    if (tree == BHS_TREE_CHAIN && (rc = build_coupling(p))) {
         bhs_plan_destroy(p);
         return rc;
     }

@@ -25,6 +25,7 @@ struct bhs_tile_hdr {
 };
 
 struct bhs_plan {
+    int tree;  // BHS_TREE_CHAIN, or BHS_TREE_HOPF: right-hand-side quadrature of the 'caa' tree, no coupling table
     int d, s_ndim, n_end, L2;
     int H, H2, Q;
     int n_bnodes;  // d - 2

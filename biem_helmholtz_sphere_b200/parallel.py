@@ -142,12 +142,14 @@ def _default_solve_shard(c, centers, radii, ks, n_end, eta, direction, x):
 
 def _default_eval_tile(c, centers, radii, k, eta, n_end, density, x_tile):
     from . import _ops
+    from ._coords import tree_spec
 
     dev = torch.device("cuda", torch.cuda.current_device())
     d = x_tile.shape[0]
-    xt = torch.as_tensor(np.asarray(x_tile), dtype=torch.float64, device=dev).reshape(d, -1).contiguous()
-    return _ops.uscat(d, n_end, torch.as_tensor(np.asarray(centers), device=dev), torch.as_tensor(np.asarray(radii), device=dev),
-                      float(k), float(eta), density.to(dev), xt)
+    axes = list(tree_spec(c).axes)  # the device code works in the chain frame of the tree
+    xt = torch.as_tensor(np.asarray(x_tile)[axes], dtype=torch.float64, device=dev).reshape(d, -1).contiguous()
+    return _ops.uscat(d, n_end, torch.as_tensor(np.asarray(centers)[:, axes], device=dev),
+                      torch.as_tensor(np.asarray(radii), device=dev), complex(k), float(eta), density.to(dev), xt)
 
 
 # ---- sharded drivers --------------------------------------------------------------------------------------------
@@ -202,7 +204,9 @@ def uscat_sharded(c: Any, *, centers, radii, k: float, eta: float, n_end: int, d
     if sl.stop > sl.start:
         u = torch.as_tensor(fn(c, centers, radii, k, eta, n_end, dens, tile)).reshape(tile.shape[1:])
     else:
-        u = torch.zeros((0,) + tuple(x_grid.shape[2:]), dtype=torch.complex128)
+        # an empty shard lives where the other ranks' tiles live, so that every rank returns a tensor of the same device
+        u = torch.zeros((0,) + tuple(x_grid.shape[2:]), dtype=torch.complex128,
+                        device=_comm_device(group) if world > 1 else dens.device)
     if not gather or world == 1:
         return u
     return all_gather_rows(u, n0, group)
@@ -216,9 +220,11 @@ def ball_rows(B: int, rank: int, world: int) -> tuple[int, int]:
 
 def _default_assemble_rows(c, centers, radii, k, eta, n_end, alpha, beta, b_lo, b_hi):
     from . import _ops
-    from ._coords import branching_types_of
+    from ._coords import tree_spec
 
-    d = len(branching_types_of(c)) + 1
+    spec = tree_spec(c)
+    d = spec.d
+    centers = np.asarray(centers)[:, list(spec.axes)]  # chain frame
     dev = torch.device("cuda", torch.cuda.current_device())
     kc = complex(k)
     kk = torch.tensor([kc.real], dtype=torch.float64, device=dev)

@@ -4,9 +4,10 @@ Restates the two batch commands of the reference CLI that produced its golden da
 and ``accuracy`` (cli.py:188-271) -- minus the typer/tqdm/matplotlib front-end: same loops, same geometries
 (``_center``, cli.py:170-185), same call into ``biem`` (plane wave built with k = 1 whatever the solve wavenumber,
 cli.py:239 vs :244), same NaN checks, same CSV columns, so that the output can be diffed row by row against
-``accuracy/*.csv`` / ``jascome/jascome_output.csv``.  Only the chain trees a / ba / bba / bbba / ... are available here.
+``accuracy/*.csv`` / ``jascome/jascome_output.csv``.  The default tree list is the reference's (cli.py:41), including the
+0 <-> d-1 leaf relabelling of the ``p`` trees (cli.py:63-69).
 
-    python -m biem_helmholtz_sphere_b200.sweeps jascome  [--out jascome_output.csv] [--branching-types a,ba,bba]
+    python -m biem_helmholtz_sphere_b200.sweeps jascome  [--out jascome_output.csv] [--branching-types a,ba,bpa,bba,bpbpa,caa]
     python -m biem_helmholtz_sphere_b200.sweeps accuracy [--out accuracy.csv] [--branching-types a] [--max-n-end 512]
 """
 
@@ -27,6 +28,8 @@ LOG = logging.getLogger(__name__)
 def _row_value(btype: str, n_end: int, k: float, half: int):
     c = create_from_branching_types(btype)
     d = c.c_ndim
+    if "p" in btype:  # swap 0 and -1, as the reference CLI does with nx.relabel_nodes (cli.py:63-69)
+        c = c.relabel({0: d - 1, d - 1: 0})
     centers = grid_centers(half, d)
     n_balls = len(centers)
     calc = _biem.biem(
@@ -43,13 +46,19 @@ def _row_value(btype: str, n_end: int, k: float, half: int):
     return n_balls, calc, complex(uscat)
 
 
-def jascome(out: str = "jascome_output.csv", branching_types: str = "a,ba,bba") -> str:
-    """Two unit spheres at (0, +-2, 0, ...), k = 1, n_end = 1..9 per tree (cli.py:36-116)."""
+JASCOME_TREES = "a,ba,bpa,bba,bpbpa,caa"  # cli.py:41
+
+
+def jascome(out: str = "jascome_output.csv", branching_types: str = JASCOME_TREES, max_n_end_4d: int | None = None) -> str:
+    """Two unit spheres at (0, +-2, 0, ...), k = 1, n_end = 1..9 per tree (cli.py:36-116).  ``max_n_end_4d`` caps the 4-D
+    trees (the reference's own 4-D runs ended at n_end = 5 / 6 when the `triplet` tensor no longer fitted its host)."""
     with open(out, "w") as f:
         f.write("branching_types,n_end,uscat,device,dtype,density_dtype,density_device,uscat_dtype,uscat_device\n")
     for btype in reversed(branching_types.split(",")):
         try:
             for n_end in range(1, 10):
+                if max_n_end_4d is not None and create_from_branching_types(btype).c_ndim >= 4 and n_end > max_n_end_4d:
+                    break
                 _, calc, uscat = _row_value(btype, n_end, 1.0, 0)
                 with open(out, "a") as f:
                     f.write(f"{btype},{n_end},{uscat},cuda,<class 'numpy.float64'>,{calc.density.dtype},cuda,"
@@ -92,7 +101,7 @@ def main(argv=None) -> None:
     sub = ap.add_subparsers(dest="cmd", required=True)
     j = sub.add_parser("jascome")
     j.add_argument("--out", default="jascome_output.csv")
-    j.add_argument("--branching-types", default="a,ba,bba")
+    j.add_argument("--branching-types", default=JASCOME_TREES)
     a = sub.add_parser("accuracy")
     a.add_argument("--out", default="accuracy.csv")
     a.add_argument("--branching-types", default="a")

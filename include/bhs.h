@@ -54,6 +54,15 @@ int bhs_device_sm_count(int *out);
  * inside ush.harmonics_translation_coef (_biem.py:697).  Built on the host in extended precision,
  * uploaded once; the coupling table is stored tile-wise for TMA staging by bhs_assemble. */
 int bhs_plan_create(int d, int n_end, bhs_plan_t **out);
+/* Coordinate trees other than the chains.  Every tree of one dimension spans the same harmonic space (degree < n_end on
+ * S^{d-1}); what a tree changes in the reference is (i) the labelling / orientation of the cartesian axes -- trees with b'
+ * nodes are chains in a permuted frame, handled by the host code -- and (ii) where ush.expand samples the sphere
+ * (_biem.py:627).  BHS_TREE_HOPF (d = 4, the reference's 'caa': type-c root over two type-a circles) builds a plan whose
+ * right-hand-side quadrature is the Hopf product rule (n_end Gauss-Legendre nodes in cos 2 theta_0, 2 n_end equispaced nodes
+ * per circle; pinned by jascome/jascome_output.csv:2-6); it serves bhs_rhs_expand / bhs_plan_quadrature only. */
+#define BHS_TREE_CHAIN 0
+#define BHS_TREE_HOPF 1
+int bhs_plan_create_tree(int d, int n_end, int tree, bhs_plan_t **out);
 void bhs_plan_destroy(bhs_plan_t *plan);
 int bhs_plan_harm(const bhs_plan_t *plan);       /* H  = number of harmonics of degree < n_end   */
 int bhs_plan_harm2(const bhs_plan_t *plan);      /* H2 = number of harmonics of degree < 2n_end-1 */

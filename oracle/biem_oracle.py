@@ -20,6 +20,7 @@ from __future__ import annotations
 
 import functools
 import math
+import re
 from dataclasses import dataclass
 from typing import Callable
 
@@ -32,54 +33,133 @@ from scipy import special as sp
 # --------------------------------------------------------------------------------------
 
 
-class OracleCoordinates:
-    """Chain coordinate tree ``'b'*(d-2) + 'a'``.
+_TOKEN = re.compile(r"bp|b'|a|b|c")
 
-    x0 = r cos t0, x1 = r sin t0 cos t1, ..., x_{d-1} = r sin t0 ... sin t_{d-2}
-    (decoded from the reference's a.svg / ba.svg / bba.svg).
+
+def _parse_tree(branching_types: str):
+    """(node types, hopf?) of a branching-types string: chains of b / b' ('bp') nodes over one a node, or 'caa'."""
+    pos, toks = 0, []
+    while pos < len(branching_types):
+        m = _TOKEN.match(branching_types, pos)
+        if not m:
+            raise ValueError(f"invalid branching types {branching_types!r}")
+        toks.append("bp" if m.group(0) in ("bp", "b'") else m.group(0))
+        pos = m.end()
+    if toks == ["c", "a", "a"]:
+        return tuple(toks), True
+    if not toks or toks[-1] != "a" or set(toks[:-1]) - {"b", "bp"}:
+        raise ValueError(f"oracle supports chains of b / bp nodes over an a node and 'caa': got {branching_types!r}")
+    return tuple(toks), False
+
+
+class OracleCoordinates:
+    """Coordinate trees of the reference's sweeps (cli.py:41): chains ``'a'``, ``'ba'``, ``'bpa'``, ``'bba'``, ``'bpbpa'``, ...
+    and the Hopf tree ``'caa'``.
+
+    type b : leaf = r cos t, sub-tree = r sin t, t in [0, pi];   type b' ('bp'): leaf = r sin t, sub-tree = r cos t,
+    t in [-pi/2, pi/2];   'caa': x = r (cos t0 cos t1, cos t0 sin t1, sin t0 cos t2, sin t0 sin t2), t0 in [0, pi/2]
+    (decoded from the reference's *.svg drawings; pinned by the golden rows of jascome_output.csv).
+    ``axes``: tree coordinate i is the caller's cartesian coordinate axes[i] (``relabel`` = the nx.relabel_nodes of
+    cli.py:63-69).  Every tree of one dimension spans the same harmonic space; the tables below (index tables, harmonics,
+    coupling coefficients) are those of the plain chain ``.chain`` in the frame ``axes`` -- what the tree changes is where
+    the right-hand-side quadrature samples the sphere.
     """
 
-    def __init__(self, branching_types: str):
-        if not branching_types or branching_types[-1] != "a" or set(branching_types[:-1]) - {"b"}:
-            raise ValueError(f"oracle supports chain types 'a','ba','bba',...: got {branching_types!r}")
+    def __init__(self, branching_types: str, axes=None):
+        self.nodes, self.hopf = _parse_tree(branching_types)
         self.branching_types_expression_str = branching_types
-        self.s_ndim = len(branching_types)
+        self.s_ndim = len(self.nodes)
         self.c_ndim = self.s_ndim + 1
+        self.chain = "b" * (self.c_ndim - 2) + "a"
         self.root = 0
+        self.axes = tuple(range(self.c_ndim)) if axes is None else tuple(int(a) for a in axes)
+        assert sorted(self.axes) == list(range(self.c_ndim))
+
+    def relabel(self, mapping: dict) -> "OracleCoordinates":
+        return OracleCoordinates(self.branching_types_expression_str, tuple(mapping.get(a, a) for a in self.axes))
+
+    @property
+    def inverse(self):
+        return tuple(int(i) for i in np.argsort(self.axes))
 
     def to_cartesian(self, spherical, as_array: bool = True):
         d = self.c_ndim
         r = spherical.get("r", 1.0)
-        out = []
-        prod = r
-        for i in range(d - 1):
-            out.append(prod * np.cos(spherical[i]))
-            prod = prod * np.sin(spherical[i])
-        out.append(prod)
+        if self.hopf:
+            c0, s0 = np.cos(spherical[0]), np.sin(spherical[0])
+            y = [r * c0 * np.cos(spherical[1]), r * c0 * np.sin(spherical[1]),
+                 r * s0 * np.cos(spherical[2]), r * s0 * np.sin(spherical[2])]
+        else:
+            y = []
+            prod = r
+            for i in range(d - 2):
+                if self.nodes[i] == "b":
+                    y.append(prod * np.cos(spherical[i]))
+                    prod = prod * np.sin(spherical[i])
+                else:
+                    y.append(prod * np.sin(spherical[i]))
+                    prod = prod * np.cos(spherical[i])
+            y.append(prod * np.cos(spherical[d - 2]))
+            y.append(prod * np.sin(spherical[d - 2]))
+        out = [None] * d
+        for i in range(d):
+            out[self.axes[i]] = y[i]
         return np.stack(np.broadcast_arrays(*out), axis=0) if as_array else dict(enumerate(out))
 
     def from_cartesian(self, x):
         d = self.c_ndim
-        x = [np.asarray(x[i], dtype=np.float64) for i in range(d)]
-        out = {}
-        tail = np.zeros_like(x[0])
-        tails = [None] * d
-        for i in range(d - 1, -1, -1):
-            tail = tail + x[i] ** 2
-            tails[i] = tail
-        out["r"] = np.sqrt(tails[0])
+        y = [np.asarray(x[self.axes[i]], dtype=np.float64) for i in range(d)]
+        if self.hopf:
+            ra, rb = np.hypot(y[0], y[1]), np.hypot(y[2], y[3])
+            return {"r": np.hypot(ra, rb), 0: np.arctan2(rb, ra), 1: np.arctan2(y[1], y[0]), 2: np.arctan2(y[3], y[2])}
+        out = chain_from_cartesian(y)
         for i in range(d - 2):
-            out[i] = np.arctan2(np.sqrt(tails[i + 1]), x[i])
-        out[d - 2] = np.arctan2(x[d - 1], x[d - 2])
+            if self.nodes[i] == "bp":
+                out[i] = np.pi / 2 - out[i]
         return out
+
+
+def chain_from_cartesian(y):
+    """Angles of the plain chain ``b...ba``: y0 = r cos t0, y1 = r sin t0 cos t1, ..., y_{d-1} = r sin t0 ... sin t_{d-2}."""
+    d = len(y)
+    y = [np.asarray(v, dtype=np.float64) for v in y]
+    out = {}
+    tail = np.zeros_like(y[0])
+    tails = [None] * d
+    for i in range(d - 1, -1, -1):
+        tail = tail + y[i] ** 2
+        tails[i] = tail
+    out["r"] = np.sqrt(tails[0])
+    for i in range(d - 2):
+        out[i] = np.arctan2(np.sqrt(tails[i + 1]), y[i])
+    out[d - 2] = np.arctan2(y[d - 1], y[d - 2])
+    return out
+
+
+def chain_to_cartesian(angles, d):
+    out = []
+    prod = 1.0
+    for i in range(d - 1):
+        out.append(prod * np.cos(angles[i]))
+        prod = prod * np.sin(angles[i])
+    out.append(prod)
+    return np.stack(np.broadcast_arrays(*out), axis=0)
 
 
 def create_from_branching_types(branching_types: str) -> OracleCoordinates:
     return OracleCoordinates(branching_types)
 
 
+def _coords(c) -> OracleCoordinates:
+    return c if isinstance(c, OracleCoordinates) else OracleCoordinates(
+        c if isinstance(c, str) else c.branching_types_expression_str, getattr(c, "axes", None))
+
+
 def _btype(c) -> str:
-    return c if isinstance(c, str) else c.branching_types_expression_str
+    """Chain tree whose tables serve ``c`` ('a', 'ba', 'bba', ...)."""
+    if isinstance(c, str) and re.fullmatch(r"b*a", c):
+        return c
+    return _coords(c).chain
 
 
 # --------------------------------------------------------------------------------------
@@ -204,11 +284,34 @@ def quadrature(btype: str, n: int):
     return [g.ravel() for g in grids], w.ravel()
 
 
+@functools.lru_cache(maxsize=None)
+def _hopf_quadrature(n: int):
+    """Product rule of the 'caa' tree: n Gauss-Legendre nodes in cos 2 t0 (surface measure sin t0 cos t0 dt0 dt1 dt2 =
+    d(cos 2 t0)/4 dt1 dt2), 2n equispaced nodes on each circle.  Returns unit vectors [4, Q] and weights [Q]."""
+    t, w0 = sp.roots_legendre(n)
+    th0 = 0.5 * np.arccos(t)
+    az = 2.0 * math.pi * np.arange(2 * n) / (2 * n)
+    T0, T1, T2 = (a.ravel() for a in np.meshgrid(th0, az, az, indexing="ij"))
+    W = (0.25 * w0[:, None, None] * np.full((1, 2 * n, 1), math.pi / n) * np.full((1, 1, 2 * n), math.pi / n)).ravel()
+    y = np.stack([np.cos(T0) * np.cos(T1), np.cos(T0) * np.sin(T1), np.sin(T0) * np.cos(T2), np.sin(T0) * np.sin(T2)])
+    return y, W
+
+
+def quadrature_nodes(c, n: int):
+    """Right-hand-side quadrature of the tree of ``c`` in its chain frame: (unit vectors [d, Q], chain angles, weights)."""
+    co = _coords(c)
+    if co.hopf:
+        y, w = _hopf_quadrature(n)
+        sph = chain_from_cartesian(list(y))
+        return y, [sph[i] for i in range(co.c_ndim - 1)], w
+    angles, w = quadrature(co.chain, n)  # b' nodes: theta' = pi/2 - theta, the same points
+    return chain_to_cartesian(angles, co.c_ndim), angles, w
+
+
 def expand(c, g_values: np.ndarray, n_end: int) -> np.ndarray:
     """f_hat[..., h] = sum_q w_q g[q, ...] conj Y_h(y_q)   (ush.expand, _biem.py:627)."""
-    btype = _btype(c)
-    angles, w = quadrature(btype, n_end)
-    Y = harmonics(btype, angles, n_end)  # [Q, H]
+    _, angles, w = quadrature_nodes(c, n_end)
+    Y = harmonics(_btype(c), angles, n_end)  # [Q, H]
     return np.einsum("q,q...,qh->...h", w, g_values, np.conj(Y))
 
 
@@ -349,8 +452,7 @@ def translation_coef(c, t: np.ndarray, k, n_end: int) -> np.ndarray:
     btype = _btype(c)
     d = len(btype) + 1
     L2 = 2 * n_end - 1
-    coords = OracleCoordinates(btype)
-    sph = coords.from_cartesian(t)
+    sph = chain_from_cartesian([t[i] for i in range(d)])  # t is given in the chain frame
     shape = sph["r"].shape
     r = sph["r"].ravel()
     ang = [sph[i].ravel() for i in range(d - 1)]
@@ -435,10 +537,9 @@ def sd_coef(d: int, n_end: int, k, eta, radii: np.ndarray) -> np.ndarray:
 
 def boundary_data(c, centers, radii, n_end, alpha, beta, uin, uin_grad):
     """g[q, b] at the quadrature directions   (_biem.py:611-624)."""
-    btype = _btype(c)
-    coords = OracleCoordinates(btype)
-    angles, _ = quadrature(btype, n_end)
-    yhat = coords.to_cartesian({i: a for i, a in enumerate(angles)})  # [d, Q]
+    co = _coords(c)
+    yhat, _, _ = quadrature_nodes(co, n_end)  # chain frame
+    yhat = yhat[list(co.inverse)]              # caller's cartesian frame, in which `centers` and the callables live
     x = radii[None, None, :] * yhat[:, :, None] + centers.T[:, None, :]  # [d, Q, B]
     g = np.zeros(x.shape[1:], dtype=np.complex128)
     if uin is not None:
@@ -465,7 +566,7 @@ def assemble(c, centers, radii, k, n_end, eta, alpha, beta) -> np.ndarray:
     A = np.zeros((B, H, B, H), dtype=np.complex128)
     if B > 1:
         bi, bj = np.nonzero(~np.eye(B, dtype=bool))
-        t = (centers[bi] - centers[bj]).T  # [d, P]  t = c_b - c_b'
+        t = (centers[bi] - centers[bj]).T[list(_coords(c).axes)]  # [d, P]  t = c_b - c_b' in the chain frame
         T = translation_coef(btype, t, k, n_end)  # [P, H', H]
         A[bi, :, bj, :] = np.swapaxes(T, -1, -2) * row_reg[bi][:, :, None] * SD[bj][:, None, :]
     for b in range(B):
@@ -488,8 +589,8 @@ def biem(
     kind: str = "outer",
     force_matrix: bool = False,
 ) -> OracleResult:
-    btype = _btype(c)
-    coords = OracleCoordinates(btype)
+    coords = _coords(c)
+    btype = coords.chain
     d = coords.c_ndim
     centers = np.asarray(centers, dtype=np.float64)
     radii = np.asarray(radii, dtype=np.float64)
@@ -508,8 +609,8 @@ def biem(
             raise ValueError("alpha is not zero, but uin is None.")
         if np.any(beta != 0) and uin_grad is None:
             raise ValueError("beta is not zero, but uin_grad is None.")
-        g = boundary_data(btype, centers, radii, n_end, alpha, beta, uin, uin_grad)
-        f_hat = expand(btype, g, n_end)  # [B, H]
+        g = boundary_data(coords, centers, radii, n_end, alpha, beta, uin, uin_grad)
+        f_hat = expand(coords, g, n_end)  # [B, H]
 
     use_matrix = (uin is None and uin_grad is None) or B > 1 or force_matrix
     if not use_matrix:
@@ -520,7 +621,7 @@ def biem(
         density = None if f_hat is None else f_hat / SD
         matrix = None
     else:
-        matrix = assemble(btype, centers, radii, k, n_end, eta, alpha, beta)
+        matrix = assemble(coords, centers, radii, k, n_end, eta, alpha, beta)
         H = deg.shape[0]
         density = None
         if f_hat is not None:
@@ -552,7 +653,7 @@ def biem_u(res: OracleResult, x, far_field: bool = False, per_ball: bool = False
     for s0 in range(0, P, chunk):
         xs = xf[:, s0 : s0 + chunk]
         rel = xs[:, :, None] - res.centers[:, None, :]  # [d, p, B]
-        sph = res.c.from_cartesian(rel)
+        sph = chain_from_cartesian([rel[a] for a in _coords(res.c).axes])  # chain frame of the tree
         r = sph["r"]
         Y = harmonics(btype, [sph[i] for i in range(d - 1)], n_end)  # [p, B, H]
         if far_field:

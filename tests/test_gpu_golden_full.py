@@ -1,6 +1,6 @@
 """Replay of the reference's golden CSVs through the public API (tools/golden_sweep.py): every 2-D row up to the
 reference's largest published run (n_end = 3444, N = 13 774, k up to 4096), every grid row (up to 256 discs), every
-forced-`triplet` row of the supported trees, and all 390 3-D rows (n_end <= 39) -- 1243 rows in total; the result of the
+forced-`triplet` row of ALL SIX trees (a, ba, bpa, bba, bpbpa, caa), and all 390 3-D rows (n_end <= 39) -- 1263 rows in total; the result of the
 last full run is also committed as profiles/r01_golden_sweep.json.  Tolerance 1e-10 relative."""
 import os
 import sys
@@ -25,7 +25,8 @@ def test_golden_csv_replay():
     r = res3["accuracy_k_ba.csv[ba]"]
     assert r["run"] == r["rows"] == 390 and r["outside_tolerance"] == 0, r
     full = gs.sweep(stride=1, max_n_end_2d=64, max_n_end_3d=16)["jascome_output.csv"]
-    assert full["run"] == full["rows"] == 24 and full["outside_tolerance"] == 0, full
+    # all 44 rows: the six trees of the reference CLI's default list (cli.py:41), incl. bpa / bpbpa / caa
+    assert full["run"] == full["rows"] == 44 and full["outside_tolerance"] == 0, full
 
 
 def test_jascome_csv_writer_matches_reference_file(tmp_path):
@@ -35,18 +36,19 @@ def test_jascome_csv_writer_matches_reference_file(tmp_path):
     from biem_helmholtz_sphere_b200 import sweeps
     from golden_util import load
 
-    out = sweeps.jascome(str(tmp_path / "jascome_output.csv"), "a,ba,bba")
+    out = sweeps.jascome(str(tmp_path / "jascome_output.csv"))  # default tree list = cli.py:41
     rows = list(csv.DictReader(open(out)))
     ref_hdr = open(os.path.join(ROOT, "tests", "golden", "jascome_output.csv")).readline().strip()
     assert open(out).readline().strip() == ref_hdr
-    assert [r["branching_types"] for r in rows] == ["bba"] * 9 + ["ba"] * 9 + ["a"] * 9  # reversed order, n_end 1..9
+    # reversed order of the default list, n_end 1..9 (the reference's own 4-D runs died at n_end 6 / 7 / 7, cli.py:113-115)
+    assert [r["branching_types"] for r in rows] == sum(([t] * 9 for t in ("caa", "bpbpa", "bba", "bpa", "ba", "a")), [])
     gold = {(r["branching_types"], r["n_end"]): r["uscat"] for r in load("jascome_output.csv")}
     tol = {6: 5e-10, 7: 1e-9, 8: 2e-9, 9: 1e-7}
     n = 0
     for r in rows:
         key = (r["branching_types"], int(r["n_end"]))
-        if key in gold:  # the reference's bba run stopped at n_end = 6
+        if key in gold:  # the reference's 4-D runs stopped at n_end = 5 (caa) and 6 (bba, bpbpa)
             v = complex(r["uscat"])
             assert abs(v - gold[key]) <= tol.get(key[1], 1e-10) * abs(gold[key]), key
             n += 1
-    assert n == 24
+    assert n == 44

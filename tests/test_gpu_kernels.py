@@ -263,6 +263,12 @@ def test_zgetrf_zgetrs_and_singular(ops):
     bufs = ops.zgetrf_(LU)
     x = ops.zgetrs_(LU, bufs, b.clone())
     assert float((A @ x - b).abs().max()) < 1e-9
+    # more right-hand sides than one warp of the permutation kernel (every column must be permuted)
+    b40 = torch.randn(N, 40, dtype=torch.complex128, device="cuda", generator=g)
+    x40 = ops.zgetrs_(LU, bufs, b40.clone())
+    assert float((A @ x40 - b40).abs().max()) < 1e-9
+    x40s, _ = ops.zgesv_(A.clone(), b40.clone())
+    assert float((A @ x40s - b40).abs().max()) < 1e-9
     S = torch.zeros(64, 64, dtype=torch.complex128, device="cuda")
     S[:40, :40] = torch.eye(40, dtype=torch.complex128, device="cuda")
     bufs2 = ops.zgetrf_(S)

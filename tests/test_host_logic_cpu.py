@@ -22,20 +22,47 @@ def test_grid_centers_match_reference_center_function():
     assert g.shape == (3, 8, 8) and g[0, 0, 0] == -20.0 and g[1, -1, -1] == 20.0 and not g[2].any()
 
 
-@pytest.mark.parametrize("bt", ["a", "ba", "bba"])
-def test_coordinate_stand_in_round_trip(bt):
+@pytest.mark.parametrize("bt", ["a", "ba", "bba", "bpa", "bpbpa", "bbpa", "caa"])
+@pytest.mark.parametrize("relabel", [False, True])
+def test_coordinate_stand_in_round_trip(bt, relabel):
+    """Every tree of the reference's sweeps (cli.py:41), with and without the CLI's 0 <-> d-1 leaf relabelling
+    (cli.py:63-69): cartesian -> angles -> cartesian, angle ranges, and agreement with the oracle's coordinates."""
     c = bhs.create_from_branching_types(bt)
-    assert c.c_ndim == len(bt) + 1 and c.s_ndim == len(bt) and c.branching_types_expression_str == bt
+    o = bo.OracleCoordinates(bt)
+    d = c.c_ndim
+    if relabel:
+        c, o = c.relabel({0: d - 1, d - 1: 0}), o.relabel({0: d - 1, d - 1: 0})
+    ntok = len(bt.replace("bp", "b"))
+    assert c.c_ndim == ntok + 1 and c.s_ndim == ntok and c.branching_types_expression_str == bt
     rng = np.random.default_rng(0)
-    x = rng.normal(size=(c.c_ndim, 50))
+    x = rng.normal(size=(d, 50))
     sph = c.from_cartesian(x)
     back = c.to_cartesian(sph)
     assert np.allclose(back, x, atol=1e-13)
-    o = bo.OracleCoordinates(bt).from_cartesian(x)
+    oo = o.from_cartesian(x)
     for k in sph:
-        assert np.allclose(sph[k], o[k])
-    with pytest.raises(NotImplementedError):
-        bhs.create_from_branching_types("caa")
+        assert np.allclose(sph[k], oo[k])
+    assert np.allclose(o.to_cartesian(oo), x, atol=1e-13)
+    for i, node in enumerate(c.nodes[:-1] if bt != "caa" else c.nodes[:1]):
+        lo, hi = {"b": (0.0, np.pi), "bp": (-np.pi / 2, np.pi / 2), "c": (0.0, np.pi / 2)}[node]
+        assert np.all(sph[i] >= lo) and np.all(sph[i] <= hi)
+    spec = c.spec
+    assert spec.d == d and len(spec.chain) == d - 1 and sorted(spec.axes) == list(range(d))
+    assert spec.tree == (1 if bt == "caa" else 0)
+    # the chain frame: x_chain = x[axes] has the plain chain's angles up to theta -> pi/2 - theta at b' nodes
+    if bt != "caa":
+        ch = bo.chain_from_cartesian([x[a] for a in spec.axes])
+        for i, node in enumerate(c.nodes[:-1]):
+            assert np.allclose(sph[i], ch[i] if node == "b" else np.pi / 2 - ch[i])
+        assert np.allclose(sph[d - 2], ch[d - 2])
+
+
+def test_coordinate_stand_in_rejects_unknown_trees():
+    for bad in ("cba", "ab", "bb", "caaa", "x"):
+        with pytest.raises((NotImplementedError, ValueError)):
+            bhs.create_from_branching_types(bad)
+    with pytest.raises(ValueError):
+        bhs.SphericalCoordinates("ba", axes=(0, 0, 1))
 
 
 def test_memory_model_and_harmonic_counts():

@@ -16,6 +16,8 @@ from golden_util import find, load
 def run(btype, n_end, k=1.0, half=0):
     c = oracle.create_from_branching_types(btype)
     d = c.c_ndim
+    if "p" in btype:  # the reference CLI swaps the cartesian leaves 0 and d - 1 of the `p` trees (cli.py:63-69)
+        c = c.relabel({0: d - 1, d - 1: 0})
     uin, _ = oracle.plane_wave(k=1.0, direction=np.array([1.0] + [0.0] * (d - 1)))  # quirk: k=1
     cen = grid_centers(half, d)
     res = oracle.biem(c, uin=uin, k=k, n_end=n_end, eta=1.0, centers=cen, radii=np.ones(len(cen)))
@@ -78,8 +80,9 @@ def test_2d_grids(half, n_end):
 TRIPLET_TOL = {1: 1e-14, 2: 1e-14, 3: 1e-14, 4: 1e-14, 5: 1e-13, 6: 5e-12, 7: 1e-10, 8: 2e-9, 9: 1e-7}
 
 
-@pytest.mark.parametrize("btype", ["a", "ba", "bba"])
+@pytest.mark.parametrize("btype", ["a", "ba", "bpa", "bba", "bpbpa", "caa"])
 def test_jascome_rows(btype):
+    """All 44 rows of jascome/jascome_output.csv, i.e. every tree of the reference CLI's default list (cli.py:41)."""
     rows = [r for r in load("jascome_output.csv") if r["branching_types"] == btype]
     assert rows
     for r in rows:

@@ -26,6 +26,8 @@ def run_row(bhs, btype, n_end, k, half):
 
     c = bhs.create_from_branching_types(btype)
     d = c.c_ndim
+    if "p" in btype:  # the reference CLI swaps the cartesian leaves 0 and d - 1 of the `p` trees (cli.py:63-69)
+        c = c.relabel({0: d - 1, d - 1: 0})
     uin = bhs.plane_wave(k=np.asarray(1.0), direction=np.asarray((1.0,) + (0.0,) * (d - 1)))[0]
     cen = grid_centers(half, d)
     calc = bhs.biem(c, uin=uin, k=np.asarray(float(k)), n_end=n_end, eta=np.asarray(1.0), centers=cen,
@@ -41,7 +43,7 @@ def sweep(stride=1, max_n_end_2d=512, max_n_end_3d=39, verbose=False):
         "accuracy_k_ba.csv[ba]": [r for r in load("accuracy_k_ba.csv") if r["branching_types"] == "ba"],
         "accuracy_k_a.csv": load("accuracy_k_a.csv"),
         "accuracy_n_balls_a.csv": load("accuracy_n_balls_a.csv"),
-        "jascome_output.csv": [r for r in load("jascome_output.csv") if r["branching_types"] in ("a", "ba", "bba")],
+        "jascome_output.csv": load("jascome_output.csv"),  # all six trees of cli.py:41: a, ba, bpa, bba, bpbpa, caa
     }
     out = {}
     for name, rows in files.items():
@@ -51,7 +53,7 @@ def sweep(stride=1, max_n_end_2d=512, max_n_end_3d=39, verbose=False):
             if i % stride:
                 continue
             bt = r.get("branching_types", "a")
-            d = len(bt) + 1
+            d = len(bt.replace("bp", "b")) + 1
             lim = max_n_end_2d if d == 2 else max_n_end_3d
             if r["n_end"] > lim:
                 n_skip += 1
