@@ -36,7 +36,8 @@ SIGNATURES = {
     "bhs_assemble_workspace": (i64, [vp, i32, i32]),
     "bhs_assemble": (i32, [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp, vp]),
     "bhs_assemble_rows": (i32, [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, i64, i64, vp, vp]),
-    "bhs_diag_coef": (i32, [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "bhs_diag_coef_workspace": (i64, [vp, i32, i32]),
+    "bhs_diag_coef": (i32, [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "bhs_zgesv_workspace": (i64, [i64, i32]),
     "bhs_zgesv": (i32, [i64, i32, vp, i64, vp, vp, vp, vp, vp]),
     "bhs_zgesv_batched_workspace": (i64, [i64, i32, i32]),

@@ -130,8 +130,9 @@ def diag_coef(d: int, n_end: int, radii, k, eta=None, alpha=None, beta=None, k_i
     be = None if beta is None else _c128(beta)
     out = torch.empty((kk.numel(), B, plan.H), dtype=C128, device=rad.device)
     kim = None if k_im is None else _f64(k_im).reshape(-1)
+    work = _work(load().bhs_diag_coef_workspace(plan.handle, B, kk.numel()))
     check(load().bhs_diag_coef(plan.handle, B, kk.numel(), ptr(rad), ptr(kk), ptr(kim), ptr(et), ptr(al), ptr(be),
-                               ptr(out), stream_ptr()), "bhs_diag_coef")
+                               ptr(out), ptr(work), stream_ptr()), "bhs_diag_coef")
     return out
 
 

@@ -418,8 +418,18 @@ struct AsmWork {
     cplx* colf;
     cplx* diag;
     int32_t *rep, *uid, *cursor, *n_unique, *grp_rep, *grp_start, *members;
+    double* scratch;  // global order-sequence scratch of the radial kernels (very high orders only), else null
     int64_t bytes;
 };
+// shape of pair_radial_kernel's order sequences (orders 0 .. L2 of the pair distances)
+static void pair_radial_shape(const bhs_plan* p, int& n_store, int& T, size_t& smem) {
+    const int d = p->d;
+    int shift = (d & 1) ? (d - 3) / 2 : d / 2 - 1;
+    n_store = p->L2 + 1 + shift;
+    T = 64;
+    while (T > 32 && (size_t)2 * n_store * T * sizeof(double) > 160 * 1024) T >>= 1;
+    smem = (size_t)2 * n_store * T * sizeof(double);
+}
 static AsmWork carve(const bhs_plan* p, int B, int nsys, void* base) {
     AsmWork w;
     unsigned char* c = (unsigned char*)base;
@@ -440,6 +450,15 @@ static AsmWork carve(const bhs_plan* p, int B, int nsys, void* base) {
     w.grp_rep = (int32_t*)take(np * 4);
     w.grp_start = (int32_t*)take((np + 1) * 4);
     w.members = (int32_t*)take(np * 4);
+    {
+        int n_store, T;
+        size_t smem;
+        pair_radial_shape(p, n_store, T, smem);
+        size_t scr = smem > 200 * 1024 ? (size_t)2 * n_store * 32 * T * sizeof(double) : 0;
+        const size_t scr_ball = ball_radial_scratch_bytes(p->d, p->n_end);
+        if (scr_ball > scr) scr = scr_ball;
+        w.scratch = scr ? (double*)take((int64_t)scr) : nullptr;
+    }
     w.bytes = off;
     return w;
 }
@@ -464,7 +483,7 @@ static int run_factors(const bhs_plan* p, int B, int nsys, const double* d_radii
         BHS_CHECK_LAUNCH();
         return BHS_OK;
     }
-    int rc = launch_ball_radial(p->d, p->n_end, B, nsys, d_radii, d_k, 0.0, w.rad, st);
+    int rc = launch_ball_radial(p->d, p->n_end, B, nsys, d_radii, d_k, 0.0, w.rad, w.scratch, st);
     if (rc) return rc;
     factors_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(p->d, p->n_end, p->H, B, nsys, d_radii, d_k, d_eta,
                                                                  (const cplx*)d_alpha, (const cplx*)d_beta, w.rad,
@@ -498,13 +517,12 @@ static int assemble_impl(const bhs_plan_t* plan, int B, int nsys, const double* 
     if (rc) return rc;
     {
         const int d = plan->d;
-        int shift = (d & 1) ? (d - 3) / 2 : d / 2 - 1;
-        int n_store = plan->L2 + 1 + shift;
-        int T = 64;
-        while (T > 32 && (size_t)2 * n_store * T * sizeof(double) > 160 * 1024) T >>= 1;
-        size_t smem = (size_t)2 * n_store * T * sizeof(double);
+        const int shift = (d & 1) ? (d - 3) / 2 : d / 2 - 1;
+        int n_store, T;
+        size_t smem;
+        pair_radial_shape(plan, n_store, T, smem);
         int64_t total = np * nsys, blocks = (total + T - 1) / T;
-        if (blocks > 148 * 8) blocks = 148 * 8;
+        if (blocks > bhs_sm_count() * 8) blocks = bhs_sm_count() * 8;
         if (d_k_im) {
             int Tz = 64;
             const int ns = plan->L2 + 1 + shift;
@@ -513,15 +531,12 @@ static int assemble_impl(const bhs_plan_t* plan, int B, int nsys, const double* 
             if (smz > 200 * 1024) return BHS_ERR_UNSUPPORTED;
             cudaFuncSetAttribute(pair_radial_z_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smz);
             int64_t bz = (total + Tz - 1) / Tz;
-            if (bz > 148 * 8) bz = 148 * 8;
+            if (bz > bhs_sm_count() * 8) bz = bhs_sm_count() * 8;
             pair_radial_z_kernel<<<(unsigned)bz, Tz, smz, st>>>(d, plan->L2, ns, B, nsys, d_k, d_k_im, w.dist, w.hp);
         } else if (smem > 200 * 1024) {
+            // very high orders: the sequences live in the workspace's global scratch
             if (blocks > 32) blocks = 32;
-            double* scratch = nullptr;
-            if (cudaMallocAsync((void**)&scratch, (size_t)2 * n_store * blocks * T * sizeof(double), st) != cudaSuccess)
-                return BHS_ERR_ALLOC;
-            pair_radial_kernel<<<(unsigned)blocks, T, 0, st>>>(d, plan->L2, n_store, B, nsys, d_k, w.dist, w.hp, scratch);
-            cudaFreeAsync(scratch, st);
+            pair_radial_kernel<<<(unsigned)blocks, T, 0, st>>>(d, plan->L2, n_store, B, nsys, d_k, w.dist, w.hp, w.scratch);
         } else {
             cudaFuncSetAttribute(pair_radial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             pair_radial_kernel<<<(unsigned)blocks, T, smem, st>>>(d, plan->L2, n_store, B, nsys, d_k, w.dist, w.hp, nullptr);
@@ -561,7 +576,7 @@ static int assemble_impl(const bhs_plan_t* plan, int B, int nsys, const double* 
     const int ntiles = plan->tiles_r * plan->tiles_c;
     // The number of distinct translations U is only known on the device: the y-dimension strides over them, sized
     // for about four waves of CTAs (4 resident per SM) and never more than the off-diagonal pair count.
-    int64_t chunks = (4 * 4 * 148 + (int64_t)ntiles * nsys - 1) / ((int64_t)ntiles * nsys);
+    int64_t chunks = (4 * 4 * bhs_sm_count() + (int64_t)ntiles * nsys - 1) / ((int64_t)ntiles * nsys);
     if (chunks < 1) chunks = 1;
     if (chunks > np - B) chunks = np - B > 0 ? np - B : 1;
     if (chunks > 65535 || nsys > 65535) return BHS_ERR_UNSUPPORTED;
@@ -601,20 +616,24 @@ extern "C" int bhs_assemble_rows(const bhs_plan_t* plan, int B, int nsys, const 
                          sys_stride, d_work, stream);
 }
 
+extern "C" int64_t bhs_diag_coef_workspace(const bhs_plan_t* plan, int B, int nsys) {
+    if (!plan || B <= 0 || nsys <= 0) return BHS_ERR_INVALID;
+    return al256((int64_t)nsys * B * plan->n_end * 4 * sizeof(cplx)) + al256((int64_t)ball_radial_scratch_bytes(plan->d, plan->n_end));
+}
+
 extern "C" int bhs_diag_coef(const bhs_plan_t* plan, int B, int nsys, const double* d_radii, const double* d_k,
                              const double* d_k_im, const double* d_eta, const double* d_alpha, const double* d_beta,
-                             double* d_out, void* stream) {
-    if (!plan || B <= 0 || nsys <= 0 || !d_radii || !d_k || !d_out) return BHS_ERR_INVALID;
-    // needs only the radial table: carve it out of a temporary allocation
+                             double* d_out, void* d_work, void* stream) {
+    if (!plan || B <= 0 || nsys <= 0 || !d_radii || !d_k || !d_out || !d_work) return BHS_ERR_INVALID;
+    // needs only the radial table (and, for very high orders, its scratch): both in the caller's workspace
     cudaStream_t st = (cudaStream_t)stream;
-    double4* rad = nullptr;
-    if (cudaMallocAsync((void**)&rad, (size_t)nsys * B * plan->n_end * 4 * sizeof(cplx), st) != cudaSuccess)
-        return BHS_ERR_ALLOC;
     AsmWork w;
-    w.rad = rad; w.rowf = nullptr; w.colf = nullptr; w.diag = (cplx*)d_out;
-    int rc = run_factors(plan, B, nsys, d_radii, d_k, d_k_im, d_eta, d_alpha, d_beta, w, true, st);
-    cudaFreeAsync(rad, st);
-    return rc;
+    w.rad = (double4*)d_work;
+    w.scratch = ball_radial_scratch_bytes(plan->d, plan->n_end)
+                    ? (double*)((unsigned char*)d_work + al256((int64_t)nsys * B * plan->n_end * 4 * sizeof(cplx)))
+                    : nullptr;
+    w.rowf = nullptr; w.colf = nullptr; w.diag = (cplx*)d_out;
+    return run_factors(plan, B, nsys, d_radii, d_k, d_k_im, d_eta, d_alpha, d_beta, w, true, st);
 }
 
 // ---- K3: right-hand side ------------------------------------------------------------------------------------

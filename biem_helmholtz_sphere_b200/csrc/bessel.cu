@@ -55,7 +55,7 @@ extern "C" int bhs_bessel(int d, int kind, int derivative, int n_max, const doub
     if (smem > 200 * 1024) return BHS_ERR_UNSUPPORTED;
     cudaFuncSetAttribute(bessel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int64_t blocks = (nx + T - 1) / T;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > bhs_sm_count() * 8) blocks = bhs_sm_count() * 8;
     bessel_kernel<<<(unsigned)blocks, T, smem, (cudaStream_t)stream>>>(d, kind, derivative, n_max, n_store, d_x, nx,
                                                                        (cplx*)d_out);
     BHS_CHECK_LAUNCH();
@@ -96,8 +96,51 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double* sink)
     if (s == 123.456) sink[0] = s;
 }
 
+// The larger PTX shapes (sm_90+).  On sm_100a ptxas lowers each of them to a sequence of DMMA.8x8x4 (2 / 4 / 8 per
+// instruction; checked with cuobjdump, profiles/r02_fp64_mma_shapes.txt): there is one native FP64 tensor operation on this
+// chip, so these measure the same pipe and only confirm that the wider shapes buy nothing.
+template <int KK>
+__global__ void __launch_bounds__(256) dmma16_peak_kernel(int iters, double* sink) {
+    double a[KK / 2], b[KK / 4];
+#pragma unroll
+    for (int i = 0; i < KK / 2; ++i) a[i] = 1.0 + (threadIdx.x + i) * 1e-9;
+#pragma unroll
+    for (int i = 0; i < KK / 4; ++i) b[i] = 0.5 + i * 1e-9;
+    double c[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) c[u][i] = 0.0;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if constexpr (KK == 4)
+                asm volatile("mma.sync.aligned.m16n8k4.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                             : "+d"(c[u][0]), "+d"(c[u][1]), "+d"(c[u][2]), "+d"(c[u][3])
+                             : "d"(a[0]), "d"(a[1]), "d"(b[0]));
+            else if constexpr (KK == 8)
+                asm volatile("mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                             : "+d"(c[u][0]), "+d"(c[u][1]), "+d"(c[u][2]), "+d"(c[u][3])
+                             : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(b[0]), "d"(b[1]));
+            else
+                asm volatile(
+                    "mma.sync.aligned.m16n8k16.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7,%8,%9,%10,%11}, "
+                    "{%12,%13,%14,%15}, {%0,%1,%2,%3};"
+                    : "+d"(c[u][0]), "+d"(c[u][1]), "+d"(c[u][2]), "+d"(c[u][3])
+                    : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(a[4]), "d"(a[5]), "d"(a[6]), "d"(a[7]), "d"(b[0]),
+                      "d"(b[1]), "d"(b[2]), "d"(b[3]));
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s += c[u][i];
+    if (s == 123.456) sink[0] = s;
+}
+
 extern "C" int bhs_fp64_peak(int shape, int iters, double* tflops_out) {
-    if (!tflops_out || iters <= 0 || shape < 0 || shape > 1) return BHS_ERR_INVALID;
+    if (!tflops_out || iters <= 0 || shape < 0 || shape > 4) return BHS_ERR_INVALID;
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -107,17 +150,23 @@ extern "C" int bhs_fp64_peak(int shape, int iters, double* tflops_out) {
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     const int blocks = sms * 4, threads = 256;
+    // flops per warp and loop iteration
+    const double per_warp[5] = {32.0 * 32.0 * 2.0, 8.0 * 512.0, 4.0 * 1024.0, 4.0 * 2048.0, 4.0 * 4096.0};
     double best = 0.0;
     for (int rep = 0; rep < 4; ++rep) {
         cudaEventRecord(e0);
-        if (shape == 0) dfma_peak_kernel<<<blocks, threads>>>(iters, sink);
-        else dmma_peak_kernel<<<blocks, threads>>>(iters, sink);
+        switch (shape) {
+            case 0: dfma_peak_kernel<<<blocks, threads>>>(iters, sink); break;
+            case 1: dmma_peak_kernel<<<blocks, threads>>>(iters, sink); break;
+            case 2: dmma16_peak_kernel<4><<<blocks, threads>>>(iters, sink); break;
+            case 3: dmma16_peak_kernel<8><<<blocks, threads>>>(iters, sink); break;
+            default: dmma16_peak_kernel<16><<<blocks, threads>>>(iters, sink); break;
+        }
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         float ms = 0;
         cudaEventElapsedTime(&ms, e0, e1);
-        double flops = (shape == 0) ? (double)blocks * threads * iters * 32.0 * 2.0
-                                    : (double)blocks * (threads / 32) * iters * 8.0 * 512.0;
+        const double flops = (double)blocks * (threads / 32) * iters * per_warp[shape];
         double tf = flops / (ms * 1e-3) * 1e-12;
         if (rep > 0 && tf > best) best = tf;
     }
@@ -167,7 +216,7 @@ extern "C" int bhs_bessel_z(int d, int kind, int derivative, int n_max, const do
     if (smem > 200 * 1024) return BHS_ERR_UNSUPPORTED;
     cudaFuncSetAttribute(bessel_z_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int64_t blocks = (nx + T - 1) / T;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > bhs_sm_count() * 8) blocks = bhs_sm_count() * 8;
     bessel_z_kernel<<<(unsigned)blocks, T, smem, (cudaStream_t)stream>>>(d, kind, derivative, n_max, n_store, d_x_re, d_x_im,
                                                                          nx, (cplx*)d_out);
     BHS_CHECK_LAUNCH();

@@ -17,6 +17,9 @@ extern unsigned long long g_bhs_launches;
         if (e__ != cudaSuccess) return (int)e__;   \
     } while (0)
 
+// number of SMs of the current device (queried once per device; grids of the persistent / capped kernels are sized from it)
+int bhs_sm_count();
+
 typedef double2 cplx;
 
 __host__ __device__ __forceinline__ cplx cmake(double re, double im) { return make_double2(re, im); }

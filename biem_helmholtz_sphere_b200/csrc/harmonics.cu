@@ -44,7 +44,7 @@ static int launch_harmonics(const bhs_plan* plan, int Lb, const int32_t* d_idx, 
     if (smem > 200 * 1024) return BHS_ERR_UNSUPPORTED;
     cudaFuncSetAttribute(harmonics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int64_t blocks = (npts + warps - 1) / warps;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > bhs_sm_count() * 16) blocks = bhs_sm_count() * 16;
     harmonics_kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(tb, Lb, d_idx, Hb, d_xyz, npts, d_scale, conj_out,
                                                                  d_out);
     BHS_CHECK_LAUNCH();

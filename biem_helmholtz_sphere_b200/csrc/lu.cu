@@ -189,10 +189,20 @@ __device__ __forceinline__ double flip_sign_if(double v, unsigned mask_hi) {
     return __hiloint2double(__double2hiint(v) ^ (int)mask_hi, __double2loint(v));
 }
 
-__global__ void __launch_bounds__(G_THREADS, 2)
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// PROD = true: no block barrier inside the k loop.  Every warp hands a finished stage back through an `empty` mbarrier (one
+// arrival per warp); one iteration LATER -- when the other warps have almost certainly arrived too -- the warps' first lanes
+// refill that stage (each its share of the nine box loads).  Prefetch distance T_STAGES - 1.
+// PROD = false: one block barrier per stage, refill right behind it.
+template <int MINB, bool PROD>
+__global__ void __launch_bounds__(G_THREADS, MINB)
     zgemm_tma_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__ CUtensorMap mapU, TmaGemmArgs g) {
     extern __shared__ unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t full[T_STAGES];
+    __shared__ __align__(8) uint64_t empty[T_STAGES];
     // 1024-byte alignment: the 128-byte swizzle pattern is a function of the shared-memory address bits 7..9
     unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     unsigned char* smA = smem;
@@ -210,7 +220,7 @@ __global__ void __launch_bounds__(G_THREADS, 2)
     // complete before its one pending arrival).
     auto issue = [&](int it, int s, int part) {
         const int kk = g.k0 + it * G_KC;
-        if (part == 0) mbar_expect_tx(&full[s], 2 * T_STAGE_BYTES);
+        if (part <= 0) mbar_expect_tx(&full[s], 2 * T_STAGE_BYTES);
         const int b0 = part < 0 ? 0 : (part == 0 ? 0 : 3 * part - 1), b1 = part < 0 ? 9 : (part == 3 ? 9 : 3 * part + 2);
         for (int b = b0; b < b1; ++b) {
             if (b == 0)
@@ -220,7 +230,10 @@ __global__ void __launch_bounds__(G_THREADS, 2)
         }
     };
     if (tid == 0) {
-        for (int s = 0; s < T_STAGES; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < T_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 4);
+        }
         mbar_fence_init();
     }
     __syncthreads();
@@ -230,27 +243,50 @@ __global__ void __launch_bounds__(G_THREADS, 2)
     double are[4][4][2], aim[4][4][2];
     const int64_t row0 = g.row_base + (int64_t)rt * G_TM + wm * 32 + (lane >> 2);
     const int64_t col0 = g.col_base + (int64_t)ct * G_TN + wn * 32 + 2 * (lane & 3);
+    // interior tiles (the great majority) skip the per-element window tests
+    const bool interior = (int64_t)trow >= g.row_lo && (int64_t)trow + G_TM <= g.row_hi && (int64_t)tcol >= g.col_lo &&
+                          (int64_t)tcol + G_TN <= g.col_hi;
+    cplx* const Cw = g.C + row0 * g.ldc + col0;
+    if (interior) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int64_t r = row0 + 8 * i;
-        const bool rv = r >= g.row_lo && r < g.row_hi;
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int64_t c = col0 + 8 * j + e;
-                cplx v = cmake(0.0, 0.0);
-                if (rv && c >= g.col_lo && c < g.col_hi) v = g.C[r * g.ldc + c];
-                are[i][j][e] = -v.x;
-                aim[i][j][e] = -v.y;
+                for (int e = 0; e < 2; ++e) {
+                    const cplx v = Cw[(int64_t)(8 * i) * g.ldc + 8 * j + e];
+                    are[i][j][e] = -v.x;
+                    aim[i][j][e] = -v.y;
+                }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int64_t r = row0 + 8 * i;
+            const bool rv = r >= g.row_lo && r < g.row_hi;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int64_t c = col0 + 8 * j + e;
+                    cplx v = cmake(0.0, 0.0);
+                    if (rv && c >= g.col_lo && c < g.col_hi) v = g.C[r * g.ldc + c];
+                    are[i][j][e] = -v.x;
+                    aim[i][j][e] = -v.y;
+                }
             }
         }
     }
     const unsigned odd_sign = (lane & 1) ? 0x80000000u : 0u;
-    const bool odd = lane & 1;
-    const int kx = (lane & 2) ? 4 : 0, rx = lane >> 2;
-    const int a_base = (wm * 32 + rx) * 128 + (lane & 1) * 8;
+    const int kx = (lane & 2) ? 4 : 0, rx = lane >> 2, odd8 = (lane & 1) * 8;
+    const int a_base = (wm * 32 + rx) * 128 + odd8;
     const int b_base = wn * 4 * 1024;
+    // byte offsets of this lane's 16-byte chunk in the four k-steps of a stage (128-byte swizzle: chunk ^ row)
+    int a_sw[4], b_sw[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        a_sw[q] = ((q + kx) ^ rx) << 4;
+        b_sw[q] = (q + kx) * 128 + ((rx ^ (q + kx)) << 4);
+    }
     for (int it = 0; it < g.nks; ++it) {
         const int s = it % T_STAGES;
         mbar_wait(&full[s], (it / T_STAGES) & 1);
@@ -258,18 +294,17 @@ __global__ void __launch_bounds__(G_THREADS, 2)
         const unsigned char* Bs = smB + s * T_STAGE_BYTES + b_base;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const int k = q + kx;  // complex k index of this lane inside the stage
             double ap[4], ac[4], bre[4], bim[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                ap[i] = *reinterpret_cast<const double*>(As + i * 1024 + ((k ^ rx) << 4));
+                ap[i] = *reinterpret_cast<const double*>(As + i * 1024 + a_sw[q]);
                 ac[i] = flip_sign_if(ap[i], odd_sign);
             }
+            // B fragments: even lanes (real k') take (re, im) of U[k][n] for the (re-tile, im-tile), odd lanes (im, re)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const double2 v = *reinterpret_cast<const double2*>(Bs + j * 1024 + k * 128 + ((rx ^ k) << 4));
-                bre[j] = odd ? v.y : v.x;
-                bim[j] = odd ? v.x : v.y;
+                bre[j] = *reinterpret_cast<const double*>(Bs + j * 1024 + b_sw[q] + odd8);
+                bim[j] = *reinterpret_cast<const double*>(Bs + j * 1024 + b_sw[q] + (8 - odd8));
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -279,11 +314,29 @@ __global__ void __launch_bounds__(G_THREADS, 2)
                     dmma884(aim[i][j][0], aim[i][j][1], ap[i], bim[j]);
                 }
         }
-        __syncthreads();
-        if (lane == 0 && it + T_STAGES < g.nks) {
-            fence_proxy_async();
-            issue(it + T_STAGES, s, warp);
+        if (PROD) {
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&empty[s]);
+                if (it >= 1 && it - 1 + T_STAGES < g.nks) {
+                    const int sp = (it - 1) % T_STAGES;
+                    mbar_wait(&empty[sp], ((it - 1) / T_STAGES) & 1);
+                    issue(it - 1 + T_STAGES, sp, warp);
+                }
+            }
+        } else {
+            __syncthreads();
+            if (lane == 0 && it + T_STAGES < g.nks) issue(it + T_STAGES, s, warp);
         }
+    }
+    if (interior) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) Cw[(int64_t)(8 * i) * g.ldc + 8 * j + e] = cmake(-are[i][j][e], -aim[i][j][e]);
+        return;
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -300,6 +353,24 @@ __global__ void __launch_bounds__(G_THREADS, 2)
     }
 }
 static const size_t T_SMEM = (size_t)T_STAGES * 2 * T_STAGE_BYTES + 1024;
+
+static int gemm_minb() {  // resident CTAs per SM the kernel is compiled for (measurement switch)
+    static const int v = [] { const char* e = getenv("BHS_GEMM_MINB"); return e ? atoi(e) : 2; }();
+    return v;
+}
+static void launch_zgemm_tma(dim3 grid, cudaStream_t st, const CUtensorMap& mL, const CUtensorMap& mU, const TmaGemmArgs& t) {
+    static bool attr_set = false;
+    static const bool prod = getenv("BHS_GEMM_BARRIER") == nullptr;  // default: barrier-free k loop (measured 3 % faster)
+    if (!attr_set) {
+        cudaFuncSetAttribute(zgemm_tma_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_SMEM);
+        cudaFuncSetAttribute(zgemm_tma_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_SMEM);
+        cudaFuncSetAttribute(zgemm_tma_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_SMEM);
+        attr_set = true;
+    }
+    if (prod) zgemm_tma_kernel<2, true><<<grid, G_THREADS, T_SMEM, st>>>(mL, mU, t);
+    else if (gemm_minb() == 3) zgemm_tma_kernel<3, false><<<grid, G_THREADS, T_SMEM, st>>>(mL, mU, t);
+    else zgemm_tma_kernel<2, false><<<grid, G_THREADS, T_SMEM, st>>>(mL, mU, t);
+}
 
 // ---- tensor maps (driver entry point fetched through the runtime: no link-time dependency on libcuda) -----------------
 typedef CUresult (*bhs_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -1268,7 +1339,7 @@ static void lu_gemm(LuCtx& x, int64_t r_lo, int64_t r_hi, int64_t c_lo, int64_t 
         t.k0 = (int)k0; t.nks = (K + G_KC - 1) / G_KC;
         dim3 grid(ct1 - t.ct0 + 1, rt1 - t.rt0 + 1, x.nbatch);
         bhs_prof_begin(pcat, x.st);
-        zgemm_tma_kernel<<<grid, G_THREADS, T_SMEM, x.st>>>(x.mapL, x.mapU, t);
+        launch_zgemm_tma(grid, x.st, x.mapL, x.mapU, t);
         bhs_prof_end(pcat, 8.0 * (double)(r_hi - r_lo) * (double)(c_hi - c_lo) * (double)K * x.nbatch, x.st);
         LU_LAUNCH_CHECK(x);
         return;
@@ -1451,7 +1522,6 @@ static void lu_rec(LuCtx& x, int64_t j0, int w) {
 static int lu_factor(LuCtx& x) {
     cudaMemsetAsync(x.info, 0, sizeof(int32_t) * x.nbatch, x.st);
     cudaFuncSetAttribute(zgemm_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
-    cudaFuncSetAttribute(zgemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_SMEM);
     cudaFuncSetAttribute(rhs_block_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM);
     // BHS_LU_GEMM_ONLY=1 (measurement aid, wrong results): issue only the trailing updates, to see how much of a
     // sweep's time the DMMA kernel accounts for on its own
@@ -1612,12 +1682,11 @@ extern "C" int bhs_zgemm_sub(int64_t M, int64_t N, int64_t K, const double* d_A,
         int rc = make_operand_map(&mL, d_A, M, K, lda, 1, 0, G_TM);
         if (rc == BHS_OK) rc = make_operand_map(&mU, d_B, K, N, ldb, 1, 0, G_KC);
         if (rc != BHS_OK) return rc;
-        cudaFuncSetAttribute(zgemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_SMEM);
         TmaGemmArgs t;
         t.C = (cplx*)d_C; t.ldc = ldc; t.row_base = 0; t.col_base = 0; t.rt0 = 0; t.ct0 = 0;
         t.row_lo = 0; t.row_hi = M; t.col_lo = 0; t.col_hi = N; t.sC = 0; t.k0 = 0; t.nks = (int)nks;
         dim3 grid((unsigned)cdiv64(N, G_TN), (unsigned)cdiv64(M, G_TM));
-        zgemm_tma_kernel<<<grid, G_THREADS, T_SMEM, st>>>(mL, mU, t);
+        launch_zgemm_tma(grid, st, mL, mU, t);
         BHS_CHECK_LAUNCH();
         return BHS_OK;
     }

@@ -81,7 +81,19 @@ extern "C" int64_t bhs_launch_count(int reset) {
     return (int64_t)v;
 }
 
-extern "C" int bhs_version(void) { return 101; }
+int bhs_sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (!cached[dev]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+extern "C" int bhs_version(void) { return 200; }
 extern "C" int bhs_device_sm_count(int* out) {
     if (!out) return BHS_ERR_INVALID;
     int dev = 0;

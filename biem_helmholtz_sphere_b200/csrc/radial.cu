@@ -34,24 +34,36 @@ __global__ void ball_radial_kernel(int d, int L, int n_store, int B, int nsys, c
     }
 }
 
-int launch_ball_radial(int d, int L, int B, int nsys, const double* d_radii, const double* d_k, double k_scalar,
-                       double4* d_out, cudaStream_t st) {
+// Order sequences of very high orders (2-D, n_end in the hundreds or thousands) do not fit in shared memory: the kernel
+// then keeps them in a global scratch that the CALLER provides (the C layer never allocates): this many bytes, 0 when the
+// shared-memory path applies.
+static void ball_radial_shape(int d, int L, int& n_store, int& T, size_t& smem) {
     int shift = (d & 1) ? (d - 3) / 2 : d / 2 - 1;
-    int n_store = L + 2 + shift + 1;
-    int T = 64;
+    n_store = L + 2 + shift + 1;
+    T = 64;
     while (T > 32 && (size_t)2 * n_store * T * sizeof(double) > 160 * 1024) T >>= 1;
-    size_t smem = (size_t)2 * n_store * T * sizeof(double);
+    smem = (size_t)2 * n_store * T * sizeof(double);
+}
+size_t ball_radial_scratch_bytes(int d, int L) {
+    int n_store, T;
+    size_t smem;
+    ball_radial_shape(d, L, n_store, T, smem);
+    return smem > 200 * 1024 ? (size_t)2 * n_store * 32 * T * sizeof(double) : 0;
+}
+
+int launch_ball_radial(int d, int L, int B, int nsys, const double* d_radii, const double* d_k, double k_scalar,
+                       double4* d_out, double* d_scratch, cudaStream_t st) {
+    int n_store, T;
+    size_t smem;
+    ball_radial_shape(d, L, n_store, T, smem);
     int64_t total = (int64_t)B * nsys;
     int64_t blocks = (total + T - 1) / T;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > bhs_sm_count() * 8) blocks = bhs_sm_count() * 8;
     if (smem > 200 * 1024) {
-        // high orders: sequences in a temporary global scratch (stream-ordered allocation, rare path)
+        // high orders: sequences in the caller's global scratch (rare path)
+        if (!d_scratch) return BHS_ERR_INVALID;
         if (blocks > 32) blocks = 32;
-        double* scratch = nullptr;
-        size_t bytes = (size_t)2 * n_store * blocks * T * sizeof(double);
-        if (cudaMallocAsync((void**)&scratch, bytes, st) != cudaSuccess) return BHS_ERR_ALLOC;
-        ball_radial_kernel<<<(unsigned)blocks, T, 0, st>>>(d, L, n_store, B, nsys, d_radii, d_k, k_scalar, d_out, scratch);
-        cudaFreeAsync(scratch, st);
+        ball_radial_kernel<<<(unsigned)blocks, T, 0, st>>>(d, L, n_store, B, nsys, d_radii, d_k, k_scalar, d_out, d_scratch);
         BHS_CHECK_LAUNCH();
         return BHS_OK;
     }
@@ -105,7 +117,7 @@ int launch_ball_radial_z(int d, int L, int B, int nsys, const double* d_radii, c
     cudaFuncSetAttribute(ball_radial_z_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int64_t total = (int64_t)B * nsys;
     int64_t blocks = (total + T - 1) / T;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > bhs_sm_count() * 8) blocks = bhs_sm_count() * 8;
     ball_radial_z_kernel<<<(unsigned)blocks, T, smem, st>>>(d, L, n_store, B, nsys, d_radii, d_kr, d_ki, kr_s, ki_s, d_out);
     BHS_CHECK_LAUNCH();
     return BHS_OK;

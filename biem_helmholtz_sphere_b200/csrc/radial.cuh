@@ -4,8 +4,10 @@
 
 // rad[(s*B + b)*L + n] = (j_n, j_n', y_n, y_n')(k_s * rho_b) for the d-dimensional hyperspherical functions
 // (d_k == nullptr: every system uses k_scalar)
+// d_scratch: ball_radial_scratch_bytes(d, L) bytes of caller-provided global memory (may be null when that is 0)
+size_t ball_radial_scratch_bytes(int d, int L);
 int launch_ball_radial(int d, int L, int B, int nsys, const double* d_radii, const double* d_k, double k_scalar,
-                       double4* d_out, cudaStream_t st);
+                       double4* d_out, double* d_scratch, cudaStream_t st);
 
 // SD_n(rho) = D - i eta S = rho^{d-1} k^{d-2} (eta j_n + i k j_n')      (_biem.py:742)
 __device__ __forceinline__ cplx sd_coef(int d, double k, double eta, double rho, double jn, double jd) {

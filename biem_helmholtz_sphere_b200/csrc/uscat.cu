@@ -617,7 +617,8 @@ extern "C" int64_t bhs_uscat_workspace(const bhs_plan_t* plan, int B) {
                  align256((int64_t)B * (4 + 2 * npair) * sizeof(double)) + 256;  // records, beta, planar records, flag
     int64_t cg = align256((int64_t)B * plan->H * sizeof(cplx));
     int64_t kbuf = 256;
-    return rad + (c3 > cg ? c3 : cg) + kbuf;
+    // + the radial kernel's global order scratch (only for orders too high for shared memory; see radial.cuh)
+    return rad + (c3 > cg ? c3 : cg) + kbuf + align256((int64_t)ball_radial_scratch_bytes(plan->d, (int)L));
 }
 
 template <int LMAX, bool ZK, bool PLANAR>
@@ -653,7 +654,8 @@ extern "C" int bhs_uscat(const bhs_plan_t* plan, int B, const double* d_centers,
     if (!plan || B <= 0 || P < 0) return BHS_ERR_INVALID;
     if (P == 0) return BHS_OK;  // empty point set: nothing to do (the buffers of empty arrays may be null)
     if (!d_centers || !d_radii || !d_density || !d_x || !d_out || !d_work) return BHS_ERR_INVALID;
-    if (!(k > 0.0)) return BHS_ERR_UNSUPPORTED;
+    // real wavenumbers must be positive; with Im k > 0 (absorbing medium) any real part is a valid argument of h^{(1)}_n
+    if (k_im == 0.0 ? !(k > 0.0) : !(k_im > 0.0 || k > 0.0)) return BHS_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     const int d = plan->d, L = plan->n_end, H = plan->H;
     const int64_t npair = (int64_t)L * (L + 1) / 2;
@@ -661,8 +663,10 @@ extern "C" int bhs_uscat(const bhs_plan_t* plan, int B, const double* d_centers,
     double4* d_rad = (double4*)(w + 256);
     unsigned char* d_coef = w + 256 + align256((int64_t)B * L * 4 * sizeof(cplx));
     const cplx* d_radz = (k_im != 0.0) ? (const cplx*)d_rad : nullptr;
+    const size_t scr = ball_radial_scratch_bytes(d, L);
+    double* d_scratch = scr ? (double*)(w + bhs_uscat_workspace(plan, B) - align256((int64_t)scr)) : nullptr;
     int rc = d_radz ? launch_ball_radial_z(d, L, B, 1, d_radii, nullptr, nullptr, k, k_im, (cplx*)d_rad, st)
-                    : launch_ball_radial(d, L, B, 1, d_radii, nullptr, k, d_rad, st);
+                    : launch_ball_radial(d, L, B, 1, d_radii, nullptr, k, d_rad, d_scratch, st);
     if (rc) return rc;
     const int far = (flags & BHS_FLAG_FAR_FIELD) ? 1 : 0;
     UscatArgs a;
@@ -691,7 +695,7 @@ extern "C" int bhs_uscat(const bhs_plan_t* plan, int B, const double* d_centers,
             // coplanar points and centres (decided on the device, no host round trip): +-m collapse, 8 instead of 12
             // FP64 instructions per (n, |m|) step
             int64_t cb = (P + 255) / 256;
-            if (cb > 148 * 4) cb = 148 * 4;
+            if (cb > bhs_sm_count() * 4) cb = bhs_sm_count() * 4;
             uscat_planar_check_kernel<<<(unsigned)cb, 256, 0, st>>>(P, d_x + 2 * P, B, d_centers, d_planar);
             BHS_CHECK_LAUNCH();
             a.planar = d_planar;
@@ -717,7 +721,7 @@ extern "C" int bhs_uscat(const bhs_plan_t* plan, int B, const double* d_centers,
     if (smem > 200 * 1024) return BHS_ERR_UNSUPPORTED;
     cudaFuncSetAttribute(uscat_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int64_t blocks = (P + warps - 1) / warps;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > bhs_sm_count() * 16) blocks = bhs_sm_count() * 16;
     bhs_prof_begin(BHS_PROF_USCAT, st);
     uscat_generic_kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(a, harm_tables_of(plan));
     bhs_prof_end(BHS_PROF_USCAT, 8.0 * (double)a.P * a.B * a.H, st);

@@ -126,10 +126,12 @@ int bhs_assemble_rows(const bhs_plan_t *plan, int B, int nsys, const double *d_c
                       const double *d_eta, const double *d_alpha, const double *d_beta, int b_lo, int b_hi,
                       double *d_A, int64_t ld, int64_t sys_stride, void *d_work, void *stream);
 
-/* single-sphere shortcut diag[s, b, h] = SD_n (alpha h_n + beta k h_n')  (_biem.py:648-691) */
+/* single-sphere shortcut diag[s, b, h] = SD_n (alpha h_n + beta k h_n')  (_biem.py:648-691);
+ * d_work: bhs_diag_coef_workspace() bytes (the library never allocates device memory inside an entry point) */
+int64_t bhs_diag_coef_workspace(const bhs_plan_t *plan, int B, int nsys);
 int bhs_diag_coef(const bhs_plan_t *plan, int B, int nsys, const double *d_radii, const double *d_k,
                   const double *d_k_im, const double *d_eta, const double *d_alpha, const double *d_beta,
-                  double *d_out, void *stream);
+                  double *d_out, void *d_work, void *stream);
 
 /* K5: dense complex128 solve, row-major, blocked LU with tournament partial pivoting, trailing
  * update on FP64 tensor cores (DMMA).  Replaces batch_tensorsolve.btensorsolve -> zgesv
