@@ -52,10 +52,12 @@ class _NS:
     def __init__(self, *arrays):
         self.kind = "numpy"
         self.device = None
+        self.pinned = False
         for a in arrays:
             if isinstance(a, torch.Tensor):
                 self.kind = "torch"
                 self.device = a.device
+                self.pinned = a.device.type == "cpu" and a.is_pinned()
                 break
 
     def out(self, t: torch.Tensor):
@@ -70,6 +72,12 @@ class _NS:
                 torch.cuda.current_stream().synchronize()
                 return host.numpy()
             return t.cpu().numpy()
+        if self.pinned and t.is_cuda:
+            # pinned host tensors in -> pinned host tensors out (one asynchronous PCIe-rate copy)
+            host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            host.copy_(t.detach(), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return host
         return t.to(self.device)
 
     def asuser(self, t: torch.Tensor):
@@ -390,7 +398,8 @@ class SweepEngine:
         self.be = torch.zeros((B,), dtype=C128, device=dev)
         self.slots = [_Slot(d, n_end, B, self.N, batch) for _ in range(nslots)]
         self.slot_bytes = nslots * batch * 16 * self.N * self.N
-        self.use_graphs = use_graphs
+        # a CUDA graph buys nothing for one huge system (C5: N = 36 864, seconds per solve) and its warm-up pass would double it
+        self.use_graphs = use_graphs and self.N <= 12000
         self.graphs_ready = False
         self.lock = threading.Lock()  # one sweep at a time per engine (slots, streams and graphs are shared state)
 

@@ -270,7 +270,7 @@ def test_matrix_only_and_errors(bhs):
         bhs.biem(c, k=np.asarray(1.0), n_end=3, centers=cen, radii=np.ones(2), eta=np.asarray(0.0))
         assert any("eigenvalue" in str(x.message) for x in w)
     with pytest.raises(NotImplementedError):
-        bhs.create_from_branching_types("caa")
+        bhs.create_from_branching_types("cba")  # general c-trees beyond the reference's own 'caa' are not implemented
 
 
 def test_per_ball_far_field_inner_point_source(bhs):

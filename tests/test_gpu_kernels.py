@@ -213,9 +213,10 @@ def test_zgesv_random(ops, N):
 
 @pytest.mark.parametrize("N,S,nrhs", [(33, 3, 1), (200, 5, 2), (515, 4, 1), (1024, 8, 1)])
 def test_zgesv_batched_equals_single(ops, N, S, nrhs):
-    """bhs_zgesv_batched (S systems in lock step, system index in blockIdx.z) against S separate bhs_zgesv calls: the
-    same kernels run on the same data, so the results must be bit-identical; systems get different pivot orders
-    (rows of system s are scaled / permuted differently)."""
+    """bhs_zgesv_batched (S systems in lock step, system index in blockIdx.z) against S separate bhs_zgesv calls; systems
+    get different pivot orders (rows of system s are scaled / permuted differently).  A lone system picks its pivots inside
+    one thread-block cluster (plain partial pivoting), systems in lock step by tournament: both are valid LU factorisations
+    of the same matrix, so the solutions agree to rounding (and are bit-identical when the tournament serves both)."""
     import torch
 
     g = torch.Generator(device="cuda").manual_seed(100 + N)
@@ -228,8 +229,11 @@ def test_zgesv_batched_equals_single(ops, N, S, nrhs):
     assert bool(torch.all(bufs.info == 0))
     for s_ in range(S):
         x1, b1 = ops.zgesv_(A[s_].clone(), b[s_].clone())
-        assert torch.equal(xb[s_], x1), f"system {s_} differs from the single-system solve"
-        assert torch.equal(bufs.ipiv[s_ * N:(s_ + 1) * N], b1.ipiv)
+        dev_ = float((xb[s_] - x1).abs().max() / x1.abs().max())
+        assert dev_ < 1e-11, f"system {s_} differs from the single-system solve by {dev_:.2e}"
+        # both pivot sequences are permutations of 0..N-1 when replayed as row swaps
+        for piv in (bufs.ipiv[s_ * N:(s_ + 1) * N], b1.ipiv):
+            assert int(piv.min()) >= 0 and int(piv.max()) < N and bool(torch.all(piv >= torch.arange(N, device="cuda")))
         rhs_s = b[s_] if nrhs > 1 else b[s_][:, None]
         xs = xb[s_] if nrhs > 1 else xb[s_][:, None]
         res = float((A[s_] @ xs - rhs_s).abs().max() / (A[s_].abs().max() * xs.abs().max() * N))
