@@ -762,6 +762,71 @@ def biem(
 # --------------------------------------------------------------------------------------------------
 # biem_u (mirror of _biem.py:822-977)
 # --------------------------------------------------------------------------------------------------
+_PIPE_MIN_POINTS = 1 << 19
+_pipe_streams: dict = {}
+
+
+def _uscat_host_pipelined(spec, d, n_end, B, cen, rad, st, dens, x, far_field, per_ball, inner, ns):
+    """Field of ONE system at host points ``x`` [d, ...]: returns the host result, or None when the point set is too small
+    (or not float64 host memory) for the tiled path to pay."""
+    if isinstance(x, torch.Tensor):
+        xh = x
+    else:
+        xa = np.asarray(x)
+        if xa.dtype != np.float64:
+            return None
+        xh = torch.from_numpy(np.ascontiguousarray(xa))
+    if xh.dtype != F64 or xh.dim() < 2 or xh.shape[0] != d:
+        return None
+    xshape = tuple(xh.shape[1:])
+    xh = xh.reshape(d, -1)
+    P = xh.shape[1]
+    if P < _PIPE_MIN_POINTS or xh.stride(1) != 1:
+        return None
+    dev = _dev()
+    key = torch.cuda.current_device()
+    if key not in _pipe_streams:
+        _pipe_streams[key] = tuple(torch.cuda.Stream(device=dev) for _ in range(3))
+    s_in, s_k, s_out = _pipe_streams[key]
+    k = (st.get("ks_host") or st["ks"].tolist())[0]
+    eta = (st.get("etas_host") or st["etas"].tolist())[0]
+    cen, rad, dens = cen.contiguous(), rad.contiguous(), dens.contiguous()
+    tail = (B,) if per_ball else ()
+    host = torch.empty((P,) + tail, dtype=C128, pin_memory=True)
+    ntile = max(2, min(16, P // (1 << 19)))
+    bounds = [P * i // ntile for i in range(ntile + 1)]
+    cur = torch.cuda.current_stream()
+    ready = torch.cuda.Event()
+    ready.record(cur)
+    for s_ in (s_in, s_k, s_out):
+        s_.wait_event(ready)
+    work = _ops._work(_ops.load().bhs_uscat_workspace(get_plan(d, n_end).handle, B))
+    keep = []
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        with torch.cuda.stream(s_in):
+            xd = torch.empty((d, hi - lo), dtype=F64, device=dev)
+            for i in range(d):  # chain frame of the tree; every row is one contiguous (pinned: asynchronous) copy
+                xd[i].copy_(xh[spec.axes[i], lo:hi], non_blocking=True)
+            e_in = torch.cuda.Event()
+            e_in.record(s_in)
+        with torch.cuda.stream(s_k):
+            s_k.wait_event(e_in)
+            od = _ops.uscat(d, n_end, cen, rad, k, eta, dens, xd, far_field=far_field, per_ball=per_ball, inner=inner,
+                            work=work)
+            e_k = torch.cuda.Event()
+            e_k.record(s_k)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(e_k)
+            host[lo:hi].copy_(od, non_blocking=True)
+        keep.append((xd, od))
+    s_out.synchronize()
+    s_k.synchronize()
+    del keep
+    host = host.reshape(xshape + tail)
+    if ns.kind == "numpy":
+        return host.numpy()
+    return host  # torch CPU callers get the pinned host tensor itself
+
 def biem_u(res: Any, x: Array, /, far_field: bool = False, per_ball: bool = False, expand_x: bool = True) -> Array:
     """Scattered field at the cartesian points ``x`` of shape ``(c_ndim, ...(x))`` (``+ ...(first)`` when
     ``expand_x`` is False); returns ``(...(x), ...(first))`` (``+ (B,)`` with ``per_ball``)."""
@@ -802,6 +867,13 @@ def biem_u(res: Any, x: Array, /, far_field: bool = False, per_ball: bool = Fals
     cen_k = cen.expand(batch_shape + (B, d)).reshape(K, B, d) if nb else cen.reshape(1, B, d)
     rad_k = rad.expand(batch_shape + (B,)).reshape(K, B) if nb else rad.reshape(1, B)
 
+    # One solved system evaluated on a large HOST point set (a heat map): tiles of points travel host -> device -> host on
+    # three streams, so that the PCIe copies of neighbouring tiles hide behind the field kernel.
+    if nb == 0 and not (isinstance(x, torch.Tensor) and x.is_cuda):
+        piped = _uscat_host_pipelined(spec, d, n_end, B, cen_k[0], rad_k[0], st, dens[0], x, far_field, per_ball,
+                                      res.kind == "inner", ns)
+        if piped is not None:
+            return piped
     xs = torch.stack([_t(x[spec.axes[i]], F64) for i in range(d)], dim=0)  # chain frame
     if expand_x or nb == 0:
         xshape = tuple(xs.shape[1:])

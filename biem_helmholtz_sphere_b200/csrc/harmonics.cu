@@ -6,6 +6,8 @@
 // (three-term recurrences, coefficients from the plan), then stream the flattened harmonics out with
 // coalesced 16-byte stores.  Replaces ush.harmonics (_biem.py:922) and the harmonics inside
 // ush.expand / ush.harmonics_translation_coef (_biem.py:627,697).
+#include <vector>
+
 #include "harmonics.cuh"
 
 __global__ void __launch_bounds__(128) harmonics_kernel(HarmTables tb, int Lb, const int32_t* __restrict__ idx,
@@ -64,4 +66,67 @@ extern "C" int bhs_harmonics(const bhs_plan_t* plan, int use_double_band, const 
 // WY[q][h] = w_q conj(Y_h(y_q)) on the RHS quadrature nodes (called once from bhs_plan_create)
 int bhs_fill_WY(bhs_plan* p) {
     return launch_harmonics(p, p->n_end, p->d_idx, p->H, p->d_qdirs, p->Q, p->d_qw, 1, p->d_WY, 0);
+}
+
+// ---- tables of the planar field kernel (3-D, n_end <= 32; called once from bhs_plan_create) ------------------------------
+// In the frame (x', y', z') = (x0, x1, x2) read as (azimuth-cos, azimuth-sin, POLAR) every direction inside the plane
+// x2 = const sits on the equator, where Y'_{n,m} = K_{n,m} e^{i m phi'} with K = 0 for n + |m| odd.  Y' is the chain harmonic
+// evaluated at the permuted vector (x2, x0, x1), so the rotation between the two bases is a quadrature away: the plan's
+// right-hand-side rule (n_end Gauss-Legendre x 2 n_end equispaced nodes) is exact for products of two harmonics of degree
+// < n_end.   rot[n][m'][m] = conj( sum_q Y'_{n,m'}(y_q) w_q conj Y_{n,m}(y_q) ),   c'_{n,m'} = sum_m rot[n][m'][m] c_{n,m}.
+__global__ void planar_rot_kernel(int L, int H, int Q, const cplx* __restrict__ Yp, const cplx* __restrict__ WY,
+                                  cplx* __restrict__ rot) {
+    const int n = blockIdx.x, w = 2 * n + 1;
+    const int64_t off = ((int64_t)4 * n * n * n - n) / 3;
+    for (int e = threadIdx.x; e < w * w; e += blockDim.x) {
+        const int r = e / w, c = e % w;
+        double sr = 0.0, si = 0.0;
+        for (int q = 0; q < Q; ++q) {
+            const cplx a = Yp[(int64_t)q * H + n * n + r], b = WY[(int64_t)q * H + n * n + c];
+            sr += a.x * b.x - a.y * b.y;
+            si += a.x * b.y + a.y * b.x;
+        }
+        rot[off + e] = cmake(sr, -si);
+    }
+    (void)L;
+}
+__global__ void planar_K_kernel(int H, const cplx* __restrict__ Yeq, double* __restrict__ K) {
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h < H) K[h] = Yeq[h].x;
+}
+
+int bhs_fill_planar_tables(bhs_plan* p) {
+    p->d_us_rot = nullptr;
+    p->d_us_K = nullptr;
+    if (p->d != 3 || p->n_end > 32 || p->tree != BHS_TREE_CHAIN) return BHS_OK;
+    const int L = p->n_end, H = p->H, Q = p->Q;
+    // quadrature directions in the permuted frame (polar <- x2, azimuth-cos <- x0, azimuth-sin <- x1), then one equator point
+    std::vector<double> dirs((size_t)3 * (Q + 1));
+    const int64_t NP = Q + 1;
+    for (int q = 0; q < Q; ++q) {
+        dirs[0 * NP + q] = p->h_qdirs[(size_t)2 * Q + q];
+        dirs[1 * NP + q] = p->h_qdirs[(size_t)0 * Q + q];
+        dirs[2 * NP + q] = p->h_qdirs[(size_t)1 * Q + q];
+    }
+    dirs[0 * NP + Q] = 0.0; dirs[1 * NP + Q] = 1.0; dirs[2 * NP + Q] = 0.0;
+    double* d_dirs = nullptr;
+    cplx* d_Y = nullptr;
+    const int64_t nrot = ((int64_t)4 * L * L * L - L) / 3;
+    int rc = BHS_OK;
+    if (cudaMalloc((void**)&d_dirs, dirs.size() * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void**)&d_Y, (size_t)NP * H * sizeof(cplx)) != cudaSuccess ||
+        cudaMalloc((void**)&p->d_us_rot, (size_t)nrot * sizeof(cplx)) != cudaSuccess ||
+        cudaMalloc((void**)&p->d_us_K, (size_t)H * sizeof(double)) != cudaSuccess)
+        rc = BHS_ERR_ALLOC;
+    if (rc == BHS_OK && cudaMemcpy(d_dirs, dirs.data(), dirs.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess)
+        rc = BHS_ERR_ALLOC;
+    if (rc == BHS_OK) rc = launch_harmonics(p, L, p->d_idx, H, d_dirs, NP, nullptr, 0, d_Y, 0);
+    if (rc == BHS_OK) {
+        planar_rot_kernel<<<L, 256>>>(L, H, Q, d_Y, p->d_WY, p->d_us_rot);
+        planar_K_kernel<<<(H + 127) / 128, 128>>>(H, d_Y + (int64_t)Q * H, p->d_us_K);
+        if (cudaDeviceSynchronize() != cudaSuccess) rc = (int)cudaGetLastError();
+    }
+    cudaFree(d_dirs);
+    cudaFree(d_Y);
+    return rc;
 }

@@ -138,7 +138,8 @@ static int upload(T** dptr, const std::vector<T>& h) {
     return BHS_OK;
 }
 
-int bhs_fill_WY(bhs_plan* p);  // harmonics.cu
+int bhs_fill_WY(bhs_plan* p);             // harmonics.cu
+int bhs_fill_planar_tables(bhs_plan* p);  // harmonics.cu
 
 // ---- coupling table -------------------------------------------------------------------------------
 struct Term {
@@ -545,7 +546,7 @@ extern "C" int bhs_plan_create_tree(int d, int n_end, int tree, bhs_plan_t** out
         bhs_plan_destroy(p);
         return rc;
     }
-    if ((rc = bhs_fill_WY(p))) {
+    if ((rc = bhs_fill_WY(p)) || (rc = bhs_fill_planar_tables(p))) {
         bhs_plan_destroy(p);
         return rc;
     }
@@ -563,7 +564,7 @@ extern "C" void bhs_plan_destroy(bhs_plan_t* p) {
     cudaFree(p->d_node_all); cudaFree(p->d_node_c1); cudaFree(p->d_node_c2);
     cudaFree(p->d_qdirs); cudaFree(p->d_qw); cudaFree(p->d_WY);
     cudaFree(p->d_tiles); cudaFree(p->d_coef); cudaFree(p->d_cidx);
-    cudaFree(p->d_us_beta); cudaFree(p->d_us_norm);
+    cudaFree(p->d_us_beta); cudaFree(p->d_us_norm); cudaFree(p->d_us_rot); cudaFree(p->d_us_K);
     delete p;
 }
 extern "C" int bhs_plan_harm(const bhs_plan_t* p) { return p ? p->H : BHS_ERR_INVALID; }

@@ -57,4 +57,9 @@ struct bhs_plan {
     // 3-D fast field-evaluation tables (monic Legendre recurrence), m-major order
     double* d_us_beta;  // [L(L+1)/2]  beta_{n,m} for the monic recurrence
     double* d_us_norm;  // [L(L+1)/2]  normalisation folded into the coefficients (incl. 1/sqrt(2pi))
+    // 3-D planar field evaluation (n_end <= 32): rotation of the harmonic coefficients into the frame whose polar axis is the
+    // normal x2 of the plane, degree blocks [(2n+1) x (2n+1)] at offset (4 n^3 - n) / 3: c'_{n,m'} = sum_m rot[n][m'][m] c_{n,m};
+    // and the equator values K_h = Y_h(theta = pi/2, phi = 0) (real; zero when n + |m| is odd)
+    cplx* d_us_rot;
+    double* d_us_K;
 };

@@ -28,6 +28,7 @@ struct UscatArgs {
     const cplx* coefg;      // generic: [B][H]
     const double* rec;      // 3-D: [B][4 + 4*npair] doubles ([B][4 + 2*npair] for the planar variant)
     const int* planar;      // 3-D: device flag, 1 = every point and every centre share the same x2 (see uscat_planar_check_kernel)
+    const double* rec3;     // 3-D planar kernel: [B][4 + 4 * planar_pairs(LMAX)] doubles
     const double* beta;     // 3-D: [npair]
     const int32_t* idx;     // [H][s]
     const int32_t* deg;     // [H]
@@ -70,10 +71,10 @@ __global__ void uscat_coef3d_kernel(int L, int LMAX, int B, double k, double k_i
     const int64_t stride = 4 + 4 * (int64_t)npair, stride2 = 4 + 2 * (int64_t)npair;
     int b = blockIdx.x;
     double* rb = rec + stride * b;
-    double* rb2 = rec2 + stride2 * b;
+    double* rb2 = rec2 ? rec2 + stride2 * b : nullptr;
     if (threadIdx.x < 4) {
         rb[threadIdx.x] = threadIdx.x < 3 ? centers[b * 3 + threadIdx.x] : radii[b];
-        rb2[threadIdx.x] = rb[threadIdx.x];
+        if (rb2) rb2[threadIdx.x] = rb[threadIdx.x];
     }
     if (b == 0 && threadIdx.x == 0) planar[0] = 1;  // cleared by uscat_planar_check_kernel on the first mismatch
     const int H = L * L;
@@ -101,7 +102,7 @@ __global__ void uscat_coef3d_kernel(int L, int LMAX, int B, double k, double k_i
         }
         reinterpret_cast<double4*>(rb + 4)[e] = out;
         // planar variant: e^{+-i m phi} are equal (phi = 0 or pi), so only c_{n,+m} + c_{n,-m} is needed
-        reinterpret_cast<double2*>(rb2 + 4)[e] = make_double2(out.x + out.z, out.y + out.w);
+        if (rb2) reinterpret_cast<double2*>(rb2 + 4)[e] = make_double2(out.x + out.z, out.y + out.w);
     }
 }
 
@@ -488,6 +489,204 @@ __global__ void __launch_bounds__(US3D_THREADS) uscat3d_kernel(UscatArgs a) {
     if (!per_ball) a.out[p] = cmake(accr, acci);
 }
 
+// ---- 3-D planar kernel ------------------------------------------------------------------------------------------------
+// Every field point and every centre share the same x2 (a heat map through coplanar spheres: the reference's plot_biem use
+// case and config C5).  In the frame whose POLAR axis is the plane's normal every direction x - c_b lies on the equator:
+//     Y'_{n,m}(pi/2, phi') = K_{n,m} e^{i m phi'},   K_{n,m} = 0 for n + |m| odd,   phi' = atan2(x1 - c1, x0 - c0),
+// so with the coefficients rotated into that frame once per ball (plan tables d_us_rot / d_us_K) there is NO Legendre
+// recurrence left and half of the (n, m) pairs vanish:
+//     u_b = sum_n h_n(k r) S_n,   S_n = sum_{m >= 0, m = n mod 2} ( A_{nm} cos m phi' + B_{nm} sin m phi' ),
+//     A = g_{n,+m} + g_{n,-m},  B = i (g_{n,+m} - g_{n,-m}),  g = K c'.
+// Per (point, ball): 4 FMAs per surviving pair (LMAX (LMAX + 2) / 4 of them: 156 at n_end = 24) + 10 per degree, against
+// 8 per (n, m) step (300 steps) of the polar-axis-in-plane form: ~2.8x fewer FP64 instructions, and no dependent chains --
+// the S_n live in registers and consecutive FMAs touch different ones.
+__host__ __device__ constexpr int planar_pairs(int LMAX) { return LMAX * (LMAX + 2) / 4; }  // LMAX even
+
+// rec3[b] = [c0, c1, c2, rho | (A.re, A.im, B.re, B.im) per pair, m-major: m = 0 .. LMAX-1, n = m, m + 2, ... < LMAX]
+__global__ void __launch_bounds__(128) uscat_coef_planar_kernel(int L, int LMAX, int B, double k, double k_im, double eta,
+                                                                const double* __restrict__ centers,
+                                                                const double* __restrict__ radii,
+                                                                const double4* __restrict__ rad, const cplx* __restrict__ radz,
+                                                                const cplx* __restrict__ rot, const double* __restrict__ K,
+                                                                const cplx* __restrict__ density, double* __restrict__ rec3) {
+    extern __shared__ __align__(16) cplx s_coef[];  // [L * L]: density * SD_n
+    const int b = blockIdx.x, H = L * L;
+    const int np = planar_pairs(LMAX);
+    double* rb = rec3 + (int64_t)(4 + 4 * np) * b;
+    if (threadIdx.x < 4) rb[threadIdx.x] = threadIdx.x < 3 ? centers[b * 3 + threadIdx.x] : radii[b];
+    for (int h = threadIdx.x; h < H; h += blockDim.x) {
+        int n = 0;
+        while ((n + 1) * (n + 1) <= h) ++n;
+        cplx sd;
+        if (radz) {
+            const cplx* rz = radz + ((int64_t)b * L + n) * 4;
+            sd = sd_coef_z(3, cmake(k, k_im), eta, radii[b], rz[0], rz[1]);
+        } else {
+            const double4 r = rad[(int64_t)b * L + n];
+            sd = sd_coef(3, k, eta, radii[b], r.x, r.y);
+        }
+        s_coef[h] = cmul(density[(int64_t)b * H + h], sd);
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < np; e += blockDim.x) {
+        int m = 0, off = 0;
+        while (off + (LMAX - m + 1) / 2 <= e) { off += (LMAX - m + 1) / 2; ++m; }
+        const int n = m + 2 * (e - off);
+        double4 out = make_double4(0.0, 0.0, 0.0, 0.0);
+        if (n < L) {
+            const int w = 2 * n + 1;
+            const cplx* blk = rot + ((int64_t)4 * n * n * n - n) / 3;
+            const cplx* cf = s_coef + n * n;
+            cplx gp = cmake(0.0, 0.0), gm = cmake(0.0, 0.0);
+            const cplx* rp = blk + (int64_t)m * w;                    // row of +m
+            const cplx* rm = blk + (int64_t)(m ? w - m : 0) * w;      // row of -m
+            for (int c = 0; c < w; ++c) {
+                gp = cfma(rp[c], cf[c], gp);
+                if (m) gm = cfma(rm[c], cf[c], gm);
+            }
+            gp = cscale(gp, K[n * n + m]);
+            gm = cscale(gm, m ? K[n * n + w - m] : 0.0);
+            // A = g+ + g-,  B = i (g+ - g-)
+            out = make_double4(gp.x + gm.x, gp.y + gm.y, -(gp.y - gm.y), gp.x - gm.x);
+        }
+        reinterpret_cast<double4*>(rb + 4)[e] = out;
+    }
+}
+
+template <int LMAX, bool ZK>
+__global__ void __launch_bounds__(US3D_THREADS, LMAX <= 24 ? 3 : 2) uscat3d_planar_kernel(UscatArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    if (a.planar[0] == 0) return;  // not coplanar: the general kernel (launched beside this one) does the work
+    const int L = a.L, B = a.B;
+    constexpr int np = planar_pairs(LMAX);
+    constexpr int rec_doubles = 4 + 4 * np;
+    double* stage0 = reinterpret_cast<double*>(smem_raw);
+    double* stage1 = stage0 + US3D_CB * rec_doubles;
+    __shared__ __align__(8) uint64_t full[2];
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int nchunks = (B + US3D_CB - 1) / US3D_CB;
+    if (tid == 0) {
+        const int nb = min(US3D_CB, B);
+        const uint32_t bytes = (uint32_t)(nb * rec_doubles * sizeof(double));
+        mbar_expect_tx(&full[0], bytes);
+        tma_load_1d(stage0, a.rec3, bytes, &full[0]);
+    }
+    const int64_t p = (int64_t)blockIdx.x * US3D_THREADS + tid;
+    const bool active = p < a.P;
+    const double x0 = active ? a.x[p] : 1e3, x1 = active ? a.x[a.P + p] : 1e3;
+    const bool inner = a.flags & BHS_FLAG_INNER, per_ball = a.flags & BHS_FLAG_PER_BALL;
+    const double k = a.k;
+    double accr = 0.0, acci = 0.0;
+    bool bad = false;
+    for (int c = 0; c < nchunks; ++c) {
+        if (tid == 0 && c + 1 < nchunks) {
+            const int nb = min(US3D_CB, B - (c + 1) * US3D_CB);
+            const uint32_t bytes = (uint32_t)(nb * rec_doubles * sizeof(double));
+            mbar_expect_tx(&full[(c + 1) & 1], bytes);
+            tma_load_1d(((c + 1) & 1) ? stage1 : stage0, a.rec3 + (int64_t)(c + 1) * US3D_CB * rec_doubles, bytes,
+                        &full[(c + 1) & 1]);
+        }
+        mbar_wait(&full[c & 1], (c >> 1) & 1);
+        const double* st = (c & 1) ? stage1 : stage0;
+        const int nb = min(US3D_CB, B - c * US3D_CB);
+        for (int bb = 0; bb < nb; ++bb) {
+            const double* rb = st + bb * rec_doubles;
+            const double4* recs = reinterpret_cast<const double4*>(rb + 4);
+            const double dx0 = x0 - rb[0], dx1 = x1 - rb[1], rho = rb[3];
+            const double r = sqrt(dx0 * dx0 + dx1 * dx1);
+            bad = bad || (inner ? (r > rho) : (r < rho));
+            const double ir = 1.0 / r;
+            const double cp = r > 0.0 ? dx0 * ir : 1.0, sp = r > 0.0 ? dx1 * ir : 0.0;
+            // angular sums S_n: every register index below is a compile-time constant (full unroll)
+            double Sr[LMAX], Si[LMAX];
+#pragma unroll
+            for (int n = 0; n < LMAX; ++n) { Sr[n] = 0.0; Si[n] = 0.0; }
+            double cm = 1.0, sm = 0.0;
+            int e = 0;
+#pragma unroll
+            for (int m = 0; m < LMAX; ++m) {
+#pragma unroll
+                for (int n = m; n < LMAX; n += 2) {
+                    const double4 ab = recs[e];
+                    ++e;
+                    Sr[n] = fma(ab.x, cm, Sr[n]);
+                    Si[n] = fma(ab.y, cm, Si[n]);
+                    if (m > 0) {
+                        Sr[n] = fma(ab.z, sm, Sr[n]);
+                        Si[n] = fma(ab.w, sm, Si[n]);
+                    }
+                }
+                const double cn = cm * cp - sm * sp;
+                sm = fma(sm, cp, cm * sp);
+                cm = cn;
+            }
+            // radial part: u_b = sum_{n < L} h_n(k r) S_n, h_n upward (orders >= L only ever meet zero sums: skipped)
+            double br, bi;
+            if (ZK) {
+                const cplx z = cmake(k * r, a.k_im * r), iz = crecip(z), ex = cexp_i(z);
+                cplx hm = cmul(cmake(ex.y, -ex.x), iz);                                       // h_0
+                cplx hc = cmul(cmul(cmake(-z.x, -z.y - 1.0), ex), cmul(iz, iz));              // h_1
+                br = hm.x * Sr[0] - hm.y * Si[0];
+                bi = hm.x * Si[0] + hm.y * Sr[0];
+#pragma unroll
+                for (int n = 1; n < LMAX; ++n) {
+                    if (n < L) {
+                        br = fma(hc.x, Sr[n], fma(-hc.y, Si[n], br));
+                        bi = fma(hc.x, Si[n], fma(hc.y, Sr[n], bi));
+                        const cplx cf = cscale(iz, 2.0 * n + 1.0);
+                        const cplx hn = cmake(fma(cf.x, hc.x, fma(-cf.y, hc.y, -hm.x)), fma(cf.x, hc.y, fma(cf.y, hc.x, -hm.y)));
+                        hm = hc;
+                        hc = hn;
+                    }
+                }
+            } else {
+                const double z = k * r, iz = 1.0 / z;
+                double s, co;
+                sincos(z, &s, &co);
+                double hmr = s * iz, hmi = -co * iz;                          // h_0
+                double hcr = (s * iz - co) * iz, hci = (-co * iz - s) * iz;   // h_1
+                br = hmr * Sr[0] - hmi * Si[0];
+                bi = hmr * Si[0] + hmi * Sr[0];
+#pragma unroll
+                for (int n = 1; n < LMAX; ++n) {
+                    if (n < L) {
+                        br = fma(hcr, Sr[n], fma(-hci, Si[n], br));
+                        bi = fma(hcr, Si[n], fma(hci, Sr[n], bi));
+                        const double cf = (2 * n + 1) * iz;
+                        const double hnr = fma(cf, hcr, -hmr), hni = fma(cf, hci, -hmi);
+                        hmr = hcr; hmi = hci;
+                        hcr = hnr; hci = hni;
+                    }
+                }
+            }
+            if (per_ball) {
+                if (active) a.out[p * B + (c * US3D_CB + bb)] = cmake(br, bi);
+            } else {
+                accr += br;
+                acci += bi;
+            }
+        }
+        __syncthreads();
+    }
+    if (!active) return;
+    if (bad) {
+        const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+        if (per_ball) {
+            for (int b = 0; b < B; ++b) a.out[p * B + b] = cmake(qnan, 0.0);
+        } else {
+            a.out[p] = cmake(qnan, 0.0);
+        }
+        return;
+    }
+    if (!per_ball) a.out[p] = cmake(accr, acci);
+}
+
 // ---- generic kernel: one warp per point ---------------------------------------------------------------
 struct SmArr {
     double* p;
@@ -613,8 +812,9 @@ extern "C" int64_t bhs_uscat_workspace(const bhs_plan_t* plan, int B) {
     if (!plan || B <= 0) return BHS_ERR_INVALID;
     int64_t L = plan->n_end, LM = (L + 7) / 8 * 8, npair = LM * (LM + 1) / 2;
     int64_t rad = align256((int64_t)B * L * 4 * sizeof(cplx));  // real (j, j', y, y') or complex (j, j', h, h') table
+    const int64_t LP = (L + 3) / 4 * 4;  // band of the planar kernel (multiple of 4)
     int64_t c3 = align256((int64_t)B * (4 + 4 * npair) * sizeof(double)) + align256(npair * sizeof(double)) +
-                 align256((int64_t)B * (4 + 2 * npair) * sizeof(double)) + 256;  // records, beta, planar records, flag
+                 align256((int64_t)B * (4 + 4 * planar_pairs((int)LP)) * sizeof(double)) + 256;  // records, beta, planar records, flag
     int64_t cg = align256((int64_t)B * plan->H * sizeof(cplx));
     int64_t kbuf = 256;
     // + the radial kernel's global order scratch (only for orders too high for shared memory; see radial.cuh)
@@ -632,16 +832,37 @@ static void launch_uscat3d_one(const UscatArgs& a, const double* rec, cudaStream
     uscat3d_kernel<LMAX, ZK, PLANAR><<<(unsigned)blocks, US3D_THREADS, smem, st>>>(b);
 }
 
-// rec2 != nullptr: the planar variant is launched as well; the device flag a.planar selects which of the two runs
+template <int LMAX, bool ZK>
+static void launch_planar_one(const UscatArgs& a, cudaStream_t st) {
+    const size_t smem = (size_t)(2 * US3D_CB * (4 + 4 * planar_pairs(LMAX))) * sizeof(double);
+    cudaFuncSetAttribute(uscat3d_planar_kernel<LMAX, ZK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int64_t blocks = (a.P + US3D_THREADS - 1) / US3D_THREADS;
+    uscat3d_planar_kernel<LMAX, ZK><<<(unsigned)blocks, US3D_THREADS, smem, st>>>(a);
+}
 template <int LMAX>
-static int launch_uscat3d(const UscatArgs& a, const double* rec2, cudaStream_t st) {
+static void launch_planar(const UscatArgs& a, cudaStream_t st) {
+    if (a.k_im != 0.0) launch_planar_one<LMAX, true>(a, st);
+    else launch_planar_one<LMAX, false>(a, st);
+}
+
+// a.rec3 != nullptr: the planar kernel is launched as well; the device flag a.planar selects which of the two does the work
+template <int LMAX>
+static int launch_uscat3d(const UscatArgs& a, cudaStream_t st) {
     bhs_prof_begin(BHS_PROF_USCAT, st);
     if (a.k_im != 0.0) launch_uscat3d_one<LMAX, true, false>(a, a.rec, st);
     else launch_uscat3d_one<LMAX, false, false>(a, a.rec, st);
     BHS_COUNT_LAUNCH();
-    if (rec2) {
-        if (a.k_im != 0.0) launch_uscat3d_one<LMAX, true, true>(a, rec2, st);
-        else launch_uscat3d_one<LMAX, false, true>(a, rec2, st);
+    if (a.rec3) {
+        switch ((a.L + 3) / 4) {
+            case 1: launch_planar<4>(a, st); break;
+            case 2: launch_planar<8>(a, st); break;
+            case 3: launch_planar<12>(a, st); break;
+            case 4: launch_planar<16>(a, st); break;
+            case 5: launch_planar<20>(a, st); break;
+            case 6: launch_planar<24>(a, st); break;
+            case 7: launch_planar<28>(a, st); break;
+            default: launch_planar<32>(a, st); break;
+        }
     }
     bhs_prof_end(BHS_PROF_USCAT, 8.0 * (double)a.P * a.B * a.H, st);
     BHS_CHECK_LAUNCH();
@@ -672,7 +893,7 @@ extern "C" int bhs_uscat(const bhs_plan_t* plan, int B, const double* d_centers,
     UscatArgs a;
     a.d = d; a.L = L; a.H = H; a.B = B; a.flags = flags; a.k = k; a.k_im = k_im; a.eta = eta;
     a.x = d_x; a.P = P; a.centers = d_centers; a.radii = d_radii;
-    a.coefg = nullptr; a.rec = nullptr; a.planar = nullptr; a.beta = plan->d_us_beta; a.idx = plan->d_idx; a.deg = plan->d_deg;
+    a.coefg = nullptr; a.rec = nullptr; a.rec3 = nullptr; a.planar = nullptr; a.beta = plan->d_us_beta; a.idx = plan->d_idx; a.deg = plan->d_deg;
     a.out = (cplx*)d_out;
     if (d == 3 && L <= 32) {
         const int LM = (L + 7) / 8 * 8;
@@ -680,32 +901,36 @@ extern "C" int bhs_uscat(const bhs_plan_t* plan, int B, const double* d_centers,
         unsigned char* q = d_coef + align256((int64_t)B * (4 + 4 * npm) * sizeof(double));
         double* d_beta = (double*)q;
         q += align256(npm * sizeof(double));
-        double* d_rec2 = (double*)q;
-        q += align256((int64_t)B * (4 + 2 * npm) * sizeof(double));
+        const int LP = (L + 3) / 4 * 4;
+        double* d_rec3 = (double*)q;
+        q += align256((int64_t)B * (4 + 4 * planar_pairs(LP)) * sizeof(double));
         int* d_planar = (int*)q;
         uscat_coef3d_kernel<<<B, 128, 0, st>>>(L, LM, B, k, k_im, eta, far, d_centers, d_radii, d_rad, d_radz,
-                                               plan->d_us_norm, (const cplx*)d_density, (double*)d_coef, d_beta, d_rec2,
+                                               plan->d_us_norm, (const cplx*)d_density, (double*)d_coef, d_beta, nullptr,
                                                d_planar);
         BHS_CHECK_LAUNCH();
         a.rec = (const double*)d_coef;
         a.beta = d_beta;
         a.planar = nullptr;
-        const double* rec2 = nullptr;
-        if (!far) {
-            // coplanar points and centres (decided on the device, no host round trip): +-m collapse, 8 instead of 12
-            // FP64 instructions per (n, |m|) step
+        if (!far && plan->d_us_rot) {
+            // coplanar points and centres (decided on the device, no host round trip): coefficients rotated into the frame
+            // whose polar axis is the plane's normal -> no Legendre recurrence, half of the (n, m) pairs vanish
             int64_t cb = (P + 255) / 256;
             if (cb > bhs_sm_count() * 4) cb = bhs_sm_count() * 4;
             uscat_planar_check_kernel<<<(unsigned)cb, 256, 0, st>>>(P, d_x + 2 * P, B, d_centers, d_planar);
             BHS_CHECK_LAUNCH();
+            uscat_coef_planar_kernel<<<B, 128, (size_t)H * sizeof(cplx), st>>>(L, LP, B, k, k_im, eta, d_centers, d_radii, d_rad,
+                                                                           d_radz, plan->d_us_rot, plan->d_us_K,
+                                                                           (const cplx*)d_density, d_rec3);
+            BHS_CHECK_LAUNCH();
             a.planar = d_planar;
-            rec2 = d_rec2;
+            a.rec3 = d_rec3;
         }
         (void)npair;
-        if (L <= 8) return launch_uscat3d<8>(a, rec2, st);
-        if (L <= 16) return launch_uscat3d<16>(a, rec2, st);
-        if (L <= 24) return launch_uscat3d<24>(a, rec2, st);
-        return launch_uscat3d<32>(a, rec2, st);
+        if (L <= 8) return launch_uscat3d<8>(a, st);
+        if (L <= 16) return launch_uscat3d<16>(a, st);
+        if (L <= 24) return launch_uscat3d<24>(a, st);
+        return launch_uscat3d<32>(a, st);
     }
     int64_t tot = (int64_t)B * H;
     uscat_coef_generic_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(d, L, H, B, k, k_im, eta, far, d_radii,

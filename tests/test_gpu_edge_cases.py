@@ -184,6 +184,43 @@ def test_uscat_planar_fast_path_selection(bhs, case, k):
         assert rel(got[~nan], want[~nan]) < 1e-11
 
 
+@pytest.mark.parametrize("n_end", [1, 3, 4, 8, 13, 17, 20, 24, 29, 32])
+@pytest.mark.parametrize("k", [1.3, 0.9 + 0.4j])
+def test_uscat_planar_kernel_every_band(bhs, n_end, k):
+    """The planar field kernel (coefficients rotated into the frame whose polar axis is the plane's normal) is instantiated
+    per band of four degrees; every band, real and complex k, outer and inner masks, against the oracle at 1e-11.  The plane
+    is x2 = -0.7 (not a coordinate plane of the centres' frame origin) and the points surround the balls (all azimuths)."""
+    from biem_helmholtz_sphere_b200 import _ops
+
+    rng = np.random.default_rng(80 + n_end)
+    B = 4
+    cen = np.array([[0.0, 2.0, -0.7], [0.5, -2.0, -0.7], [4.0, 0.3, -0.7], [-3.5, -0.4, -0.7]])
+    rad = np.array([1.0, 0.8, 1.2, 0.9])
+    deg = bo.degree_table("ba", n_end)
+    dens = (rng.normal(size=(B, n_end * n_end)) + 1j * rng.normal(size=(B, n_end * n_end))) * (0.55 ** deg)[None, :]
+    x = rng.uniform(-7, 7, size=(3, 300))
+    x[2] = -0.7
+    x[:, 0] = [0.0 + 2.5, 2.0, -0.7]   # on the x0 line through ball 0's centre (phi' = 0)
+    x[:, 1] = [0.0, 2.0 - 2.5, -0.7]   # phi' = -pi/2
+    res = bo.OracleResult(c=bo.OracleCoordinates("ba"), centers=cen.T.copy(), radii=rad, k=k, n_end=n_end, eta=0.8,
+                          kind="outer", density=dens, matrix=None)
+    for pb in (False, True):
+        want = bo.biem_u(res, x, per_ball=pb)
+        got = _ops.uscat(3, n_end, cen, rad, k, 0.8, dens, x, per_ball=pb).cpu().numpy()
+        nan = np.isnan(want)
+        assert np.array_equal(nan, np.isnan(got)) and nan.any() and not nan.all()
+        assert rel(got[~nan], want[~nan]) < 1e-11
+    # inner problem: one ball, points inside it, in its equatorial plane
+    xi = cen[0][:, None] + np.vstack([rng.uniform(-0.6, 0.6, size=(2, 50)), np.zeros((1, 50))])
+    res_i = bo.OracleResult(c=bo.OracleCoordinates("ba"), centers=cen[:1].T.copy(), radii=rad[:1], k=k, n_end=n_end, eta=0.8,
+                            kind="inner", density=dens[:1], matrix=None)
+    want = bo.biem_u(res_i, xi)
+    got = _ops.uscat(3, n_end, cen[:1], rad[:1], k, 0.8, dens[:1], xi, inner=True).cpu().numpy()
+    ok = ~np.isnan(want)
+    assert np.array_equal(np.isnan(got), ~ok)
+    assert float(np.max(np.abs(got[ok] - want[ok]) / np.abs(want[ok]))) < 1e-10
+
+
 @pytest.mark.parametrize("alpha,beta", [(1.0, 0.0), (0.0, 1.0), (1.0, 0.5 + 0.2j)])
 def test_boundary_condition_residual_on_the_spheres(bhs, alpha, beta):
     """Physics check that does not go through the oracle: the total field u_in + u_s of the GPU solution must
