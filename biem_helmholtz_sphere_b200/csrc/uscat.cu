@@ -59,7 +59,7 @@ __global__ void uscat_coef_generic_kernel(int d, int L, int H, int B, double k, 
     coefg[i] = c;
 }
 // 3-D records, m-major over the PADDED band LMAX (multiple of 8, >= L): per ball [c0, c1, c2, rho] then for
-// (m, n = m..LMAX-1): (c_{n,+m}, c_{n,-m}) * SD_n * norm_{n,m}, zero for n >= L.  Block 0 also writes the
+// (m, n = m..LMAX-1): (A, B) = (c_{n,+m} + c_{n,-m}, i (c_{n,+m} - c_{n,-m})) * SD_n * norm_{n,m}, zero for n >= L.  Block 0 also writes the
 // recurrence coefficients beta_{n,m} = (n^2 - m^2) / (4 n^2 - 1) in the same (m, n) order.
 __global__ void uscat_coef3d_kernel(int L, int LMAX, int B, double k, double k_im, double eta, int far,
                                     const double* __restrict__ centers, const double* __restrict__ radii,
@@ -98,11 +98,12 @@ __global__ void uscat_coef3d_kernel(int L, int LMAX, int B, double k, double k_i
             if (far) sd = cmul_ipow(sd, -n);
             cplx cp = cmul(density[(int64_t)b * H + n * n + m], sd);
             cplx cm = (m == 0) ? cmake(0.0, 0.0) : cmul(density[(int64_t)b * H + n * n + 2 * n + 1 - m], sd);
-            out = make_double4(cp.x, cp.y, cm.x, cm.y);
+            // A = c+ + c-,  B = i (c+ - c-):  c+ e^{i m phi} + c- e^{-i m phi} = A cos m phi + B sin m phi
+            out = make_double4(cp.x + cm.x, cp.y + cm.y, -(cp.y - cm.y), cp.x - cm.x);
         }
         reinterpret_cast<double4*>(rb + 4)[e] = out;
         // planar variant: e^{+-i m phi} are equal (phi = 0 or pi), so only c_{n,+m} + c_{n,-m} is needed
-        if (rb2) reinterpret_cast<double2*>(rb2 + 4)[e] = make_double2(out.x + out.z, out.y + out.w);
+        if (rb2) reinterpret_cast<double2*>(rb2 + 4)[e] = make_double2(out.x, out.y);
     }
 }
 
@@ -121,24 +122,20 @@ __global__ void uscat_planar_check_kernel(int64_t P, const double* __restrict__ 
 }
 
 // ---- 3-D fast kernel --------------------------------------------------------------------------------
-// One step n = N of the Legendre recurrence at fixed m (entered Duff-style at case m).  The two recurrence
-// registers swap roles with the parity of N so that no register moves are needed; every index is a
+// u_b = sum_n h_n(k r) S_n,   S_n = sum_{m >= 0} P~_n^m(cos theta) ( A_{nm} cos m phi + B_{nm} sin m phi ),
+// A = c_{n,+m} + c_{n,-m},  B = i (c_{n,+m} - c_{n,-m})  (normalisation and SD_n folded into A, B).
+// One step n = N of the Legendre recurrence at fixed m (entered Duff-style at case m): 8 FP64 instructions -- the azimuthal
+// combination w = A cm + B sm (4), S_N += q w (2), the recurrence (2).  The S_n are distinct registers, so the only dependent
+// chain is the recurrence itself; h_n is generated once per (point, ball) AFTER the angular sums and never stored.
+// The two recurrence registers swap roles with the parity of N so that no register moves are needed; every index is a
 // compile-time immediate on top of the per-m base pointers.
 #define US_ACC(Q)                                                               \
     {                                                                           \
-        const double gr = hr[(N_) < LMAX ? (N_) : 0] * (Q);                     \
-        const double gi = hi[(N_) < LMAX ? (N_) : 0] * (Q);                     \
-        if (PLANAR) {                                                           \
-            const double2 cd = recs2_m[N_];                                     \
-            tpr = fma(gr, cd.x, tpr); tpi = fma(gr, cd.y, tpi);                 \
-            tpr = fma(-gi, cd.y, tpr); tpi = fma(gi, cd.x, tpi);                \
-        } else {                                                                \
-            const double4 cc = recs_m[N_];                                      \
-            tpr = fma(gr, cc.x, tpr); tpi = fma(gr, cc.y, tpi);                 \
-            tmr = fma(gr, cc.z, tmr); tmi = fma(gr, cc.w, tmi);                 \
-            tpr = fma(-gi, cc.y, tpr); tpi = fma(gi, cc.x, tpi);                \
-            tmr = fma(-gi, cc.w, tmr); tmi = fma(gi, cc.z, tmi);                \
-        }                                                                       \
+        const double4 ab = recs_m[N_];                                          \
+        const double wr = fma(ab.z, sm, ab.x * cm);                             \
+        const double wi = fma(ab.w, sm, ab.y * cm);                             \
+        Sr[N_] = fma((Q), wr, Sr[N_]);                                          \
+        Si[N_] = fma((Q), wi, Si[N_]);                                          \
     }
 #define US_STEP(N)                                                              \
     us_l##N:                                                                    \
@@ -154,14 +151,14 @@ __global__ void uscat_planar_check_kernel(int64_t P, const double* __restrict__ 
             }                                                                   \
         }
 
-template <int LMAX, bool ZK, bool PLANAR>
+template <int LMAX, bool ZK>
 __global__ void __launch_bounds__(US3D_THREADS) uscat3d_kernel(UscatArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // the general and the planar variant are both launched; the device flag decides which one does the work
-    if (a.planar && (a.planar[0] != 0) != PLANAR) return;
+    // this kernel and the planar one are both launched; the device flag decides which one does the work
+    if (a.planar && a.planar[0] != 0) return;
     const int L = a.L, B = a.B;
     constexpr int npair = LMAX * (LMAX + 1) / 2;
-    constexpr int rec_doubles = 4 + (PLANAR ? 2 : 4) * npair;
+    constexpr int rec_doubles = 4 + 4 * npair;
     double* stage0 = reinterpret_cast<double*>(smem_raw);
     double* stage1 = stage0 + US3D_CB * rec_doubles;
     double* sbeta = stage1 + US3D_CB * rec_doubles;
@@ -222,58 +219,17 @@ __global__ void __launch_bounds__(US3D_THREADS) uscat3d_kernel(UscatArgs a) {
                     sp = dx2 * irxy;
                 }
             }
-            if (PLANAR) cp = dx1 < 0.0 ? -1.0 : 1.0;  // dx2 == 0 exactly: the azimuth is 0 or pi
-            // radial part: h_n(kr) upward (far field: the (-i)^n is folded into the coefficients)
-            double hr[LMAX], hi[LMAX];
-            if (far) {
+            // angular sums S_n (registers, static indices)
+            double Sr[LMAX], Si[LMAX];
 #pragma unroll
-                for (int n = 0; n < LMAX; ++n) { hr[n] = 1.0; hi[n] = 0.0; }
-            } else if (ZK) {
-                // complex wavenumber: h_0 = -i e^{iz}/z, h_1 = -(z + i) e^{iz}/z^2, complex upward recurrence
-                const cplx z = cmake(k * r, a.k_im * r), iz = crecip(z), e = cexp_i(z);
-                cplx h0 = cmul(cmake(e.y, -e.x), iz);
-                cplx h1 = cmul(cmul(cmake(-z.x, -z.y - 1.0), e), cmul(iz, iz));
-                hr[0] = h0.x; hi[0] = h0.y;
-                if (LMAX > 1) { hr[1] = h1.x; hi[1] = h1.y; }
-#pragma unroll
-                for (int n = 1; n < LMAX - 1; ++n) {
-                    if (n + 1 < L) {
-                        const cplx cf = cscale(iz, 2.0 * n + 1.0);
-                        hr[n + 1] = fma(cf.x, hr[n], fma(-cf.y, hi[n], -hr[n - 1]));
-                        hi[n + 1] = fma(cf.x, hi[n], fma(cf.y, hr[n], -hi[n - 1]));
-                    } else {
-                        hr[n + 1] = 0.0; hi[n + 1] = 0.0;
-                    }
-                }
-            } else {
-                const double z = k * r, iz = 1.0 / z;
-                double s, co;
-                sincos(z, &s, &co);
-                hr[0] = s * iz; hi[0] = -co * iz;
-                if (LMAX > 1) { hr[1] = (s * iz - co) * iz; hi[1] = (-co * iz - s) * iz; }
-#pragma unroll
-                for (int n = 1; n < LMAX - 1; ++n) {
-                    // orders n >= L only ever meet zero coefficients; clamp them so that nothing overflows
-                    if (n + 1 < L) {
-                        const double cf = (2 * n + 1) * iz;
-                        hr[n + 1] = fma(cf, hr[n], -hr[n - 1]);
-                        hi[n + 1] = fma(cf, hi[n], -hi[n - 1]);
-                    } else {
-                        hr[n + 1] = 0.0; hi[n + 1] = 0.0;
-                    }
-                }
-            }
-            double br = 0.0, bi = 0.0;   // this ball's sum
+            for (int n = 0; n < LMAX; ++n) { Sr[n] = 0.0; Si[n] = 0.0; }
             double qmm = 1.0, cm = 1.0, sm = 0.0;
             for (int m = 0; m < L; ++m) {
                 // q_{m-1} = 0, q_m = sin^m; the register holding the current value depends on the parity of m
                 double qa = (m & 1) ? 0.0 : qmm, qb = (m & 1) ? qmm : 0.0;
-                double tpr = 0.0, tpi = 0.0, tmr = 0.0, tmi = 0.0;
                 const int off = m * LMAX - (m * (m - 1)) / 2 - m;
-                const double4* recs_m = recs + off;                                          // general: (c+, c-)
-                const double2* recs2_m = reinterpret_cast<const double2*>(rb + 4) + off;     // planar: c+ + c-
+                const double4* recs_m = recs + off;  // (A, B) of (m, n >= m)
                 const double* beta_m = sbeta + off;
-                (void)recs_m; (void)recs2_m;
                 // binary dispatch to the Duff entry point n = m (a switch compiles to a linear compare chain here)
                 if (m < 16) {
                     if (m < 8) {
@@ -432,20 +388,57 @@ __global__ void __launch_bounds__(US3D_THREADS) uscat3d_kernel(UscatArgs a) {
                 US_STEP(29)
                 US_STEP(30)
                 US_STEP(31)
-                if (PLANAR) {
-                    // phi = 0 or pi: e^{+-i m phi} = cp^m (real), T = T+ + T-
-                    br = fma(tpr, cm, br);
-                    bi = fma(tpi, cm, bi);
-                    cm *= cp;
-                } else {
-                    // (T+ e^{i m phi} + T- e^{-i m phi})
-                    br += (tpr + tmr) * cm - (tpi - tmi) * sm;
-                    bi += (tpi + tmi) * cm + (tpr - tmr) * sm;
+                {
                     const double cn = cm * cp - sm * sp;
-                    sm = sm * cp + cm * sp;
+                    sm = fma(sm, cp, cm * sp);
                     cm = cn;
                 }
                 qmm *= sn;
+            }
+            // radial part: u_b = sum_{n < L} h_n(k r) S_n, h_n upward (far field: h_n -> 1, the (-i)^n is in the coefficients)
+            double br, bi;
+            if (far) {
+                br = 0.0; bi = 0.0;
+#pragma unroll
+                for (int n = 0; n < LMAX; ++n) {
+                    if (n < L) { br += Sr[n]; bi += Si[n]; }
+                }
+            } else if (ZK) {
+                const cplx z = cmake(k * r, a.k_im * r), iz = crecip(z), ex = cexp_i(z);
+                cplx hm = cmul(cmake(ex.y, -ex.x), iz);                                       // h_0 = -i e^{iz} / z
+                cplx hc = cmul(cmul(cmake(-z.x, -z.y - 1.0), ex), cmul(iz, iz));              // h_1 = -(z + i) e^{iz} / z^2
+                br = hm.x * Sr[0] - hm.y * Si[0];
+                bi = hm.x * Si[0] + hm.y * Sr[0];
+#pragma unroll
+                for (int n = 1; n < LMAX; ++n) {
+                    if (n < L) {
+                        br = fma(hc.x, Sr[n], fma(-hc.y, Si[n], br));
+                        bi = fma(hc.x, Si[n], fma(hc.y, Sr[n], bi));
+                        const cplx cf = cscale(iz, 2.0 * n + 1.0);
+                        const cplx hn = cmake(fma(cf.x, hc.x, fma(-cf.y, hc.y, -hm.x)), fma(cf.x, hc.y, fma(cf.y, hc.x, -hm.y)));
+                        hm = hc;
+                        hc = hn;
+                    }
+                }
+            } else {
+                const double z = k * r, iz = 1.0 / z;
+                double s, co;
+                sincos(z, &s, &co);
+                double hmr = s * iz, hmi = -co * iz;                          // h_0
+                double hcr = (s * iz - co) * iz, hci = (-co * iz - s) * iz;   // h_1
+                br = hmr * Sr[0] - hmi * Si[0];
+                bi = hmr * Si[0] + hmi * Sr[0];
+#pragma unroll
+                for (int n = 1; n < LMAX; ++n) {
+                    if (n < L) {
+                        br = fma(hcr, Sr[n], fma(-hci, Si[n], br));
+                        bi = fma(hcr, Si[n], fma(hci, Sr[n], bi));
+                        const double cf = (2 * n + 1) * iz;
+                        const double hnr = fma(cf, hcr, -hmr), hni = fma(cf, hci, -hmi);
+                        hmr = hcr; hmi = hci;
+                        hcr = hnr; hci = hni;
+                    }
+                }
             }
             if (far) {
                 // (ik)^{-1} exp(-i k x.c_b), x as given (_biem.py:931-944)
@@ -821,15 +814,13 @@ extern "C" int64_t bhs_uscat_workspace(const bhs_plan_t* plan, int B) {
     return rad + (c3 > cg ? c3 : cg) + kbuf + align256((int64_t)ball_radial_scratch_bytes(plan->d, (int)L));
 }
 
-template <int LMAX, bool ZK, bool PLANAR>
-static void launch_uscat3d_one(const UscatArgs& a, const double* rec, cudaStream_t st) {
+template <int LMAX, bool ZK>
+static void launch_uscat3d_one(const UscatArgs& a, cudaStream_t st) {
     const int npair = LMAX * (LMAX + 1) / 2;
-    size_t smem = (size_t)(2 * US3D_CB * (4 + (PLANAR ? 2 : 4) * npair) + npair) * sizeof(double);
-    cudaFuncSetAttribute(uscat3d_kernel<LMAX, ZK, PLANAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    size_t smem = (size_t)(2 * US3D_CB * (4 + 4 * npair) + npair) * sizeof(double);
+    cudaFuncSetAttribute(uscat3d_kernel<LMAX, ZK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int64_t blocks = (a.P + US3D_THREADS - 1) / US3D_THREADS;
-    UscatArgs b = a;
-    b.rec = rec;
-    uscat3d_kernel<LMAX, ZK, PLANAR><<<(unsigned)blocks, US3D_THREADS, smem, st>>>(b);
+    uscat3d_kernel<LMAX, ZK><<<(unsigned)blocks, US3D_THREADS, smem, st>>>(a);
 }
 
 template <int LMAX, bool ZK>
@@ -849,8 +840,8 @@ static void launch_planar(const UscatArgs& a, cudaStream_t st) {
 template <int LMAX>
 static int launch_uscat3d(const UscatArgs& a, cudaStream_t st) {
     bhs_prof_begin(BHS_PROF_USCAT, st);
-    if (a.k_im != 0.0) launch_uscat3d_one<LMAX, true, false>(a, a.rec, st);
-    else launch_uscat3d_one<LMAX, false, false>(a, a.rec, st);
+    if (a.k_im != 0.0) launch_uscat3d_one<LMAX, true>(a, st);
+    else launch_uscat3d_one<LMAX, false>(a, st);
     BHS_COUNT_LAUNCH();
     if (a.rec3) {
         switch ((a.L + 3) / 4) {
