@@ -25,6 +25,7 @@ from ._biem import (
     point_source,
 )
 from ._coords import SphericalCoordinates, create_from_branching_types
+from .fields import far_field_pattern, heatmap_field
 
 __all__ = [
     "BIEMKwargs",
@@ -39,4 +40,6 @@ __all__ = [
     "point_source",
     "SphericalCoordinates",
     "create_from_branching_types",
+    "heatmap_field",
+    "far_field_pattern",
 ]

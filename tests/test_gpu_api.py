@@ -303,3 +303,40 @@ def test_per_ball_far_field_inner_point_source(bhs):
     xi = cen[0][:, None] + probe_points(d, 30, 0.9, seed=3)
     ui = calc_in.uscat(xi)
     assert np.array_equal(np.isnan(ui), np.linalg.norm(xi - cen[0][:, None], axis=0) > rad[0])
+
+
+@pytest.mark.parametrize("btype", ["a", "ba"])
+def test_plot_shaped_callers_match_oracle(bhs, btype):
+    """heatmap_field / far_field_pattern return what the reference's plot_biem / plot_biem_far feed to plotly
+    (plot.py:82 uscat(per_ball=True), :187 uscat(per_ball=True, far_field=True)): checked against the oracle's per-ball
+    fields on the same grids, including the incident field, the ball selection mask, the time frames and the NaN mask."""
+    c = bhs.create_from_branching_types(btype)
+    d = c.c_ndim
+    cen = np.zeros((3, d))
+    cen[:, 0] = [0.0, 0.4, 3.1]
+    cen[:, 1] = [2.0, -2.0, 0.2]
+    rad = np.array([1.0, 0.8, 1.1])
+    k = np.asarray(1.4)
+    dirn = np.eye(d)[0]
+    uin, _ = bhs.plane_wave(k=k, direction=dirn)
+    n_end = 12
+    calc = bhs.biem(c, uin=uin, k=k, n_end=n_end, eta=np.asarray(1.0), centers=cen, radii=rad, keep_matrix=False)
+    ouin, _ = bo.plane_wave(k=1.4, direction=dirn)
+    ref = bo.biem(btype, centers=cen, radii=rad, k=1.4, n_end=n_end, uin=ouin, eta=1.0)
+    hm = bhs.heatmap_field(calc, xspace=(-5, 5, 41), yspace=(-4, 4, 33), n_t=3, plot_uscateach=[True, False, True])
+    assert hm["uscateach"].shape == (41, 33, 3) and hm["uplot_re"].shape == (3, 41, 33)
+    want_each = ref.uscat(hm["cartesian"], per_ball=True)
+    nan = np.isnan(want_each)
+    assert np.array_equal(nan, np.isnan(hm["uscateach"])) and nan.any()
+    assert rel(hm["uscateach"][~nan], want_each[~nan]) < TOL
+    u_tot = ouin(hm["cartesian"]) + want_each[..., 0] + want_each[..., 2]
+    t = np.arange(3)[:, None, None] / 3
+    want_re = np.real(u_tot[None] * np.exp(-2j * np.pi * t))
+    ok = ~np.isnan(want_re)
+    assert np.array_equal(~ok, np.isnan(hm["uplot_re"])) and rel(hm["uplot_re"][ok], want_re[ok]) < 1e-9
+    assert hm["title"].startswith("Incident Field + Scattered Field by Ball 0, 2<br>") and f"type {btype} coordinates" in hm["title"]
+    ff = bhs.far_field_pattern(calc, n_points=48)
+    want_far = ref.uscat(ff["cartesian"], per_ball=True, far_field=True)
+    assert ff["uscateach"].shape == (48, 3) and rel(ff["uscateach"], want_far) < TOL
+    assert rel(ff["uplot_abs"], np.abs(want_far.sum(-1))) < TOL
+    assert ff["title"].startswith("Far Field Pattern by Ball 0, 1, 2<br>")

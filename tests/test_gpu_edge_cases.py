@@ -252,3 +252,136 @@ def test_boundary_condition_residual_on_the_spheres(bhs, alpha, beta):
     # Dirichlet: floor = aliasing error of the reference's n_end-point RHS quadrature (4.7e-9 here); with beta != 0 the
     # one-sided difference formula dominates (1.8e-7 / 1.7e-6 measured)
     assert worst < (5e-8 if beta == 0.0 else 1e-5)
+
+
+@pytest.mark.parametrize("btype,relabel", [("bpa", True), ("bpa", False), ("bpbpa", True), ("caa", False), ("bbpa", True)])
+def test_other_trees_generic_callables_and_frames(bhs, btype, relabel):
+    """b' / c trees through the public API against the oracle, with a NON-tagged incident field (the boundary
+    data is sampled by calling back into Python: the quadrature points and normals must reach the callables in the caller's
+    cartesian frame, not in the chain frame the device code works in), Robin data, off-axis geometry and a field evaluation
+    away from the origin -- none of which the golden rows (symmetric geometry, origin only) can see."""
+    c = bhs.create_from_branching_types(btype)
+    o = bo.OracleCoordinates(btype)
+    d = c.c_ndim
+    if relabel:
+        c, o = c.relabel({0: d - 1, d - 1: 0}), o.relabel({0: d - 1, d - 1: 0})
+    rng = np.random.default_rng(len(btype) + d)
+    cen = rng.normal(size=(2, d)) * 0.4
+    cen[0, 0] += 2.2
+    cen[1, 1] -= 2.3
+    rad = np.array([1.0, 0.8])
+    dirn = rng.normal(size=d)
+    dirn /= np.linalg.norm(dirn)
+    k, n_end = 1.2, 5
+    alpha, beta = 1.0, 0.3 + 0.1j
+
+    def uin(x):
+        dd = dirn[(slice(None),) + (None,) * (x.ndim - 1)]
+        return np.exp(1j * k * np.sum(dd * x, axis=0))
+
+    def uin_grad(x):
+        dd = dirn[(slice(None),) + (None,) * (x.ndim - 1)]
+        return 1j * k * dd * uin(x)[None]
+
+    calc = bhs.biem(c, uin=uin, uin_grad=uin_grad, k=np.asarray(k), n_end=n_end, eta=np.asarray(0.9), centers=cen, radii=rad,
+                    alpha=alpha, beta=beta, keep_matrix=False)
+    ref = bo.biem(o, centers=cen, radii=rad, k=k, n_end=n_end, uin=uin, uin_grad=uin_grad, eta=0.9, alpha=alpha, beta=beta)
+    x = rng.uniform(-4, 4, size=(d, 60))
+    u, ur = np.asarray(calc.uscat(x)), ref.uscat(x)
+    ok = ~np.isnan(ur)
+    assert np.array_equal(np.isnan(u), ~ok) and ok.sum() > 20
+    assert rel(u[ok], ur[ok]) < TOL
+    # the tagged plane wave (fused right-hand side kernel) must agree with the callback path
+    pw, pwg = bhs.plane_wave(k=np.asarray(k), direction=dirn)
+    calc2 = bhs.biem(c, uin=pw, uin_grad=pwg, k=np.asarray(k), n_end=n_end, eta=np.asarray(0.9), centers=cen, radii=rad,
+                     alpha=alpha, beta=beta, keep_matrix=False)
+    assert rel(np.asarray(calc2.uscat(x))[ok], ur[ok]) < TOL
+    assert np.array_equal(np.asarray(calc.centers), cen.T)  # stored as given (transposed), in the caller's frame
+
+
+def test_evolved_record_uses_its_public_fields(bhs):
+    """attrs.evolve(res, density=...) must evaluate the NEW density (the device-side cache of biem() is not carried over),
+    as the reference's biem_u, which always reads the public fields, does."""
+    import attrs
+
+    c = bhs.create_from_branching_types("ba")
+    cen = bo.grid_centers(0, 3)
+    k = np.asarray(1.0)
+    uin = bhs.plane_wave(k=k, direction=np.eye(3)[0])[0]
+    calc = bhs.biem(c, uin=uin, k=k, n_end=5, centers=cen, radii=np.ones(2), keep_matrix=False)
+    x = np.array([[0.3, 3.0], [0.1, -0.5], [2.5, 0.7]])
+    u1 = np.asarray(calc.uscat(x))
+    doubled = attrs.evolve(calc, density=2.0 * np.asarray(calc.density))
+    assert rel(np.asarray(doubled.uscat(x)), 2.0 * u1) < 1e-13
+    moved = attrs.evolve(calc, radii=np.array([0.5, 0.5]))
+    ref = bo.OracleResult(c=bo.OracleCoordinates("ba"), centers=cen.T.copy(), radii=np.array([0.5, 0.5]), k=1.0, n_end=5,
+                          eta=1.0, kind="outer", density=np.asarray(calc.density), matrix=None)
+    assert rel(np.asarray(moved.uscat(x)), ref.uscat(x)) < TOL
+
+
+def test_singular_system_raises_or_poisons(bhs):
+    """An exactly singular system (alpha = beta = 0: the whole matrix vanishes): LinAlgError for NumPy callers, as the
+    reference's solve raises; NaN densities (no host synchronisation) for torch callers."""
+    import torch
+
+    c = bhs.create_from_branching_types("ba")
+    cen = bo.grid_centers(0, 3)
+    k = np.asarray(1.0)
+    uin = bhs.plane_wave(k=k, direction=np.eye(3)[0])[0]
+    with pytest.raises(np.linalg.LinAlgError):
+        bhs.biem(c, uin=uin, k=k, n_end=4, centers=cen, radii=np.ones(2), alpha=0.0, beta=0.0, keep_matrix=False)
+    kt = torch.tensor([1.0, 2.0], dtype=torch.float64, device="cuda")
+    uin_t = bhs.plane_wave(k=kt, direction=torch.tensor([[1.0], [0.0], [0.0]], dtype=torch.float64, device="cuda"))[0]
+    res = bhs.biem(c, uin=uin_t, k=kt, n_end=4, centers=torch.as_tensor(cen, device="cuda")[None],
+                   radii=torch.ones(1, 2, dtype=torch.float64, device="cuda"), alpha=0.0, beta=0.0, keep_matrix=False)
+    assert bool(torch.isnan(res.density.real).all())
+
+
+def test_pinned_host_tensors_in_and_out(bhs):
+    """Pinned torch CPU tensors in -> pinned torch CPU tensors out (the tiled host pipeline of large field evaluations and
+    the asynchronous result copies), same values as the NumPy path."""
+    import torch
+
+    c = bhs.create_from_branching_types("ba")
+    cen = bo.grid_centers(1, 3)
+    k = np.asarray(1.1)
+    uin = bhs.plane_wave(k=k, direction=np.eye(3)[0])[0]
+    calc = bhs.biem(c, uin=uin, k=k, n_end=8, centers=cen, radii=np.ones(4), keep_matrix=False)
+    g = np.linspace(-9, 9, 800)
+    x = np.zeros((3, 800, 800))
+    x[0], x[1] = g[:, None], g[None, :]
+    x[2] = 0.25  # off the plane of the centres: the general kernel, tiled over the three copy / compute streams
+    xp = torch.as_tensor(x).pin_memory()
+    u_pin = calc.uscat(xp)
+    assert isinstance(u_pin, torch.Tensor) and u_pin.device.type == "cpu" and u_pin.is_pinned() and u_pin.shape == (800, 800)
+    u_np = np.asarray(calc.uscat(x))
+    assert np.array_equal(np.isnan(u_np), np.isnan(u_pin.numpy()))
+    ok = ~np.isnan(u_np)
+    assert np.array_equal(u_np[ok], u_pin.numpy()[ok])
+    sub = (slice(None), slice(0, 800, 37), slice(0, 800, 41))
+    ref = bo.OracleResult(c=bo.OracleCoordinates("ba"), centers=cen.T.copy(), radii=np.ones(4), k=1.1, n_end=8, eta=1.0,
+                          kind="outer", density=np.asarray(calc.density), matrix=None)
+    want = ref.uscat(x[sub])
+    okw = ~np.isnan(want)
+    assert rel(u_np[sub[1:]][okw], want[okw]) < TOL
+
+
+def test_complex_wavenumber_with_nonpositive_real_part(bhs):
+    """Im k > 0 makes any Re k a valid argument of h^(1)_n (absorbing / evanescent media): bhs_uscat accepts it (3-D)."""
+    from biem_helmholtz_sphere_b200 import _ops
+
+    rng = np.random.default_rng(3)
+    n_end, B = 9, 2
+    cen = np.array([[0.0, 2.0, 0.1], [0.3, -2.0, -0.2]])
+    rad = np.array([1.0, 0.9])
+    dens = (rng.normal(size=(B, n_end * n_end)) + 1j * rng.normal(size=(B, n_end * n_end))) * (0.5 ** bo.degree_table("ba", n_end))
+    x = rng.uniform(-5, 5, size=(3, 200))
+    for k in (-0.4 + 1.1j, 0.0 + 0.8j):
+        res = bo.OracleResult(c=bo.OracleCoordinates("ba"), centers=cen.T.copy(), radii=rad, k=k, n_end=n_end, eta=0.7,
+                              kind="outer", density=dens, matrix=None)
+        want = bo.biem_u(res, x)
+        got = _ops.uscat(3, n_end, cen, rad, k, 0.7, dens, x).cpu().numpy()
+        ok = ~np.isnan(want)
+        assert np.array_equal(np.isnan(got), ~ok) and rel(got[ok], want[ok]) < TOL
+    with pytest.raises(NotImplementedError):
+        _ops.uscat(3, n_end, cen, rad, -1.0, 0.7, dens, x)
