@@ -20,7 +20,8 @@
 #define LU_NB 32     // panel width
 #define LU_NBO 128   // outer block width
 #define LU_R 128     // rows per tournament CTA
-#define LU_DBLK (LU_NB * LU_NB + 16)  // complex slots per system: factored diagonal block + the panel's net row map (64 ints)
+#define LU_DBLK (LU_NB * LU_NB)  // complex slots per system: factored diagonal block of the current panel
+#define LU_PMAP (2 * LU_NB)     // ints per panel: its net row map (kept for every panel: look-ahead applies them late)
 #define G_TM 64
 #define G_TN 64
 #define G_KC 8
@@ -42,6 +43,7 @@ struct LuBatch {
     int64_t sIpiv;  // pivots (int32)
     int64_t sCand;  // tournament candidate lists (int32)
     int64_t sDblk;  // factored diagonal block scratch (complex)
+    int64_t sPmap;  // net row maps of all panels (int32)
     int64_t sLp;    // packed L image (double)
     int64_t sUp;    // packed U image (double)
 };
@@ -464,6 +466,7 @@ struct SelectFinal {
     int32_t* ipiv;
     int32_t* info;
     cplx* dblk;
+    int32_t* pmap;  // this panel's slot of the row-map array
 };
 
 // 1 / p without the two divisions of Smith's algorithm when |p|^2 can neither overflow nor underflow
@@ -524,7 +527,7 @@ __device__ __forceinline__ void select_finish(const SelectFinal& fin, int w, con
     __syncthreads();
     // net effect of those swaps, for lu_permute_kernel: position j + q receives row s_win[q]; a row j + t of the
     // diagonal block that was pushed out ends at where_top[t] >= j + w
-    int32_t* pmap = (int32_t*)(fin.dblk + LU_NB * LU_NB);
+    int32_t* pmap = fin.pmap;
     if (tid < LU_NB) {
         pmap[tid] = (tid < w && s_win[tid] >= 0) ? s_win[tid] : j0 + tid;
         pmap[LU_NB + tid] = (tid < w && where_top[tid] >= j0 + w) ? where_top[tid] : -1;
@@ -558,6 +561,7 @@ __global__ void __launch_bounds__(LU_R * SEL_Q)
         fin.ipiv += (int64_t)blockIdx.z * bs.sIpiv;
         fin.info += blockIdx.z;
         fin.dblk += (int64_t)blockIdx.z * bs.sDblk;
+        fin.pmap += (int64_t)blockIdx.z * bs.sPmap;
     }
     constexpr int SEL_LC = LU_NB / SEL_Q, SEL_THREADS = LU_R * SEL_Q;
     constexpr int NW = SEL_THREADS / 32;
@@ -679,6 +683,7 @@ __global__ void __launch_bounds__(LU_R) lu_select_unrolled_kernel(const cplx* __
         fin.ipiv += (int64_t)blockIdx.z * bs.sIpiv;
         fin.info += blockIdx.z;
         fin.dblk += (int64_t)blockIdx.z * bs.sDblk;
+        fin.pmap += (int64_t)blockIdx.z * bs.sPmap;
     }
     constexpr int NW = LU_R / 32;
     __shared__ cplx prow[2][NW][LU_NB];
@@ -835,6 +840,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1)
     fin.ipiv += (int64_t)blockIdx.z * bs.sIpiv;
     fin.info += blockIdx.z;
     fin.dblk += (int64_t)blockIdx.z * bs.sDblk;
+    fin.pmap += (int64_t)blockIdx.z * bs.sPmap;
     __shared__ cplx prow[2][CP_NW][LU_NB];
     __shared__ cplx prinv[2][CP_NW];
     __shared__ unsigned long long wkey[2][CP_NW];
@@ -970,25 +976,28 @@ __global__ void __launch_bounds__(CP_THREADS, 1)
     }
 }
 
-// Apply the row interchanges of one panel to the matrix (and, in the same launch, to the right-hand sides) from the
-// panel's NET row map: all the rows of the diagonal block go through a shared-memory tile, so that every global load
-// is independent (the LAPACK-style sequence of 32 swaps is a chain of 32 dependent round trips per column).  64
-// columns per CTA, 4 threads per column.  The panel's own columns [j, j+w) of rows [j, j+w) receive the factored
-// diagonal block produced by the last tournament round.
+// Apply the row interchanges of `npan` consecutive panels (the first at column j0, 32 wide except possibly the last) to the
+// matrix columns [c_lo, c_lo + ncols) (and, in the same launch, to the right-hand sides) from the panels' NET row maps: all
+// the rows of a diagonal block go through a shared-memory tile, so that every global load is independent (the LAPACK-style
+// sequence of 32 swaps is a chain of 32 dependent round trips per column).  64 columns per CTA, 4 threads per column.
+// A panel's own columns [j, j+w) of rows [j, j+w) receive the factored diagonal block produced by the pivot-selection kernel
+// (dblk != nullptr: only when one panel is applied right after its selection).  With look-ahead the panels of a block column
+// are applied to the columns left and right of it later, several at once.
 #define PERM_COLS 64
-__global__ void __launch_bounds__(256) lu_permute_kernel(cplx* __restrict__ M, int64_t ld, int64_t ncols, int nct,
-                                                         cplx* __restrict__ rhs, int nrhs, int64_t j, int w,
-                                                         const cplx* __restrict__ dblk, int64_t sM, int64_t sRhs,
-                                                         int64_t sDblk) {
+__global__ void __launch_bounds__(256) lu_permute_kernel(cplx* __restrict__ M, int64_t ld, int64_t c_lo, int64_t ncols, int nct,
+                                                         cplx* __restrict__ rhs, int nrhs, int64_t j0, int npan, int wlast,
+                                                         const cplx* __restrict__ dblk, const int32_t* __restrict__ pmap0,
+                                                         int64_t sM, int64_t sRhs, int64_t sDblk, int64_t sPmap) {
     __shared__ cplx tile[LU_NB][PERM_COLS];
     __shared__ int32_t s_map[2 * LU_NB];
-    dblk += (int64_t)blockIdx.z * sDblk;
-    const int32_t* pmap = (const int32_t*)(dblk + LU_NB * LU_NB);
-    int64_t c0 = (int64_t)blockIdx.x * PERM_COLS;
+    if (dblk) dblk += (int64_t)blockIdx.z * sDblk;
+    pmap0 += (int64_t)blockIdx.z * sPmap;
+    int64_t c0 = c_lo + (int64_t)blockIdx.x * PERM_COLS;
+    int64_t c_end = c_lo + ncols;
     if ((int)blockIdx.x >= nct) {  // right-hand-side columns
         M = rhs + (int64_t)blockIdx.z * sRhs;
         ld = nrhs;
-        ncols = nrhs;
+        c_end = nrhs;
         c0 = (int64_t)((int)blockIdx.x - nct) * PERM_COLS;
         dblk = nullptr;
     } else {
@@ -996,35 +1005,40 @@ __global__ void __launch_bounds__(256) lu_permute_kernel(cplx* __restrict__ M, i
     }
     const int tid = threadIdx.x, col = tid & (PERM_COLS - 1), q0 = (tid / PERM_COLS) * (LU_NB / 4);
     const int64_t c = c0 + col;
-    const bool valid = c < ncols;
-    if (tid < 2 * LU_NB) s_map[tid] = pmap[tid];
-    if (valid) {
+    const bool valid = c < c_end;
+    for (int p = 0; p < npan; ++p) {
+        const int64_t j = j0 + (int64_t)p * LU_NB;
+        const int w = (p == npan - 1) ? wlast : LU_NB;
+        if (p) __syncthreads();  // the previous panel's maps and tile have been consumed
+        if (tid < 2 * LU_NB) s_map[tid] = pmap0[p * LU_PMAP + tid];
+        if (valid) {
 #pragma unroll
-        for (int i = 0; i < LU_NB / 4; ++i)
-            if (q0 + i < w) tile[q0 + i][col] = M[(j + q0 + i) * ld + c];
-    }
-    __syncthreads();
-    cplx v[LU_NB / 4];
-    if (valid) {
+            for (int i = 0; i < LU_NB / 4; ++i)
+                if (q0 + i < w) tile[q0 + i][col] = M[(j + q0 + i) * ld + c];
+        }
+        __syncthreads();
+        cplx v[LU_NB / 4];
+        if (valid) {
 #pragma unroll
-        for (int i = 0; i < LU_NB / 4; ++i) {
-            const int q = q0 + i;
-            if (q < w) {
-                const int64_t src = s_map[q];
-                v[i] = (src < j + w) ? tile[src - j][col] : M[src * ld + c];
+            for (int i = 0; i < LU_NB / 4; ++i) {
+                const int q = q0 + i;
+                if (q < w) {
+                    const int64_t src = s_map[q];
+                    v[i] = (src < j + w) ? tile[src - j][col] : M[src * ld + c];
+                }
             }
         }
-    }
-    __syncthreads();  // the rows read above are overwritten below, possibly by another thread of the column
-    if (valid) {
-        const bool in_panel = dblk != nullptr && c >= j && c < j + w;
+        __syncthreads();  // the rows read above are overwritten below, possibly by another thread of the column
+        if (valid) {
+            const bool in_panel = dblk != nullptr && c >= j && c < j + w;
 #pragma unroll
-        for (int i = 0; i < LU_NB / 4; ++i) {
-            const int q = q0 + i;
-            if (q < w) {
-                M[(j + q) * ld + c] = in_panel ? dblk[q * LU_NB + (c - j)] : v[i];
-                const int64_t dst = s_map[LU_NB + q];
-                if (dst >= 0) M[dst * ld + c] = tile[q][col];
+            for (int i = 0; i < LU_NB / 4; ++i) {
+                const int q = q0 + i;
+                if (q < w) {
+                    M[(j + q) * ld + c] = in_panel ? dblk[q * LU_NB + (c - j)] : v[i];
+                    const int64_t dst = s_map[LU_NB + q];
+                    if (dst >= 0) M[dst * ld + c] = tile[q][col];
+                }
             }
         }
     }
@@ -1269,7 +1283,9 @@ struct LuCtx {
     int32_t* ipiv;
     int32_t* info;
     int32_t* cand[2];
-    cplx* dblk;  // [LU_NB][LU_NB] factored diagonal block handed from the last tournament round to lu_permute_kernel (+ the net row map)
+    cplx* dblk;  // [LU_NB][LU_NB] factored diagonal block handed from the pivot-selection kernel to lu_permute_kernel
+    int32_t* pmaps;  // [ceil(N / 32)][LU_PMAP] net row maps of every panel
+    bool lookahead;  // panels of block J+1 on the caller's stream while the trailing update of block J runs on a side stream
     double* Lp;
     double* Up;
     int nks_total;      // LU_NBO / G_KC
@@ -1291,9 +1307,10 @@ struct LuWork {
     int32_t* cand0;
     int32_t* cand1;
     cplx* dblk;
+    int32_t* pmaps;
     double* Lp;
     double* Up;
-    int64_t ncand, sLp, sUp;
+    int64_t ncand, sLp, sUp, sPmap;
     int64_t bytes;
 };
 static LuWork lu_carve(int64_t N, int nbatch, void* base) {
@@ -1305,6 +1322,8 @@ static LuWork lu_carve(int64_t N, int nbatch, void* base) {
     w.cand0 = (int32_t*)take(w.ncand * 4 * nbatch);
     w.cand1 = (int32_t*)take(w.ncand * 4 * nbatch);
     w.dblk = (cplx*)take((int64_t)LU_DBLK * sizeof(cplx) * nbatch);
+    w.sPmap = cdiv64(N, LU_NB) * LU_PMAP;
+    w.pmaps = (int32_t*)take(w.sPmap * 4 * nbatch);
     int64_t rtiles = cdiv64(N, G_TM) + 1, ctiles = cdiv64(N, G_TN) + 1;
     int nks = LU_NBO / G_KC;
     w.sLp = rtiles * nks * G_A_STAGE;
@@ -1419,7 +1438,8 @@ static void lu_panel(LuCtx& x, int64_t j, int w) {
     int64_t nsets = cdiv64(M, LU_R);
     int cur = 0;
     bhs_prof_begin(BHS_PROF_LU_PANEL, x.st);
-    const SelectFinal fin{j, x.ipiv, x.info, x.dblk}, nofin{0, nullptr, nullptr, nullptr};
+    int32_t* const pmap_j = x.pmaps + (j / LU_NB) * LU_PMAP;
+    const SelectFinal fin{j, x.ipiv, x.info, x.dblk, pmap_j}, nofin{0, nullptr, nullptr, nullptr, nullptr};
     const bool quad = x.nbatch == 1;  // 4 lanes per candidate row for a lone system (latency); unrolled one-lane form in a sweep
     auto select_round = [&](const int32_t* rows_in, int64_t n_in, int64_t ns, int32_t* rows_out, const SelectFinal& f) {
         if (quad)
@@ -1476,9 +1496,13 @@ static void lu_panel(LuCtx& x, int64_t j, int w) {
         }
     }
     {
-        const int nct = (int)cdiv64(x.N, PERM_COLS), nrt = x.rhs ? (int)cdiv64(x.nrhs, PERM_COLS) : 0;
-        lu_permute_kernel<<<dim3((unsigned)(nct + nrt), 1, x.nbatch), 256, 0, x.st>>>(x.A, x.ld, x.N, nct, x.rhs, x.nrhs, j, w, x.dblk,
-                                                                                      x.bs.sA, x.bs.sRhs, x.bs.sDblk);
+        // row interchanges: every column (and the right-hand sides) now -- or, with look-ahead, only the columns of the outer
+        // block being factorised; the columns left and right of it follow on the side stream (lu_permute_deferred)
+        const int64_t c_lo = x.lookahead ? x.J : 0;
+        const int64_t c_hi = x.lookahead ? (x.J + LU_NBO < x.N ? x.J + LU_NBO : x.N) : x.N;
+        const int nct = (int)cdiv64(c_hi - c_lo, PERM_COLS), nrt = x.rhs ? (int)cdiv64(x.nrhs, PERM_COLS) : 0;
+        lu_permute_kernel<<<dim3((unsigned)(nct + nrt), 1, x.nbatch), 256, 0, x.st>>>(
+            x.A, x.ld, c_lo, c_hi - c_lo, nct, x.rhs, x.nrhs, j, 1, w, x.dblk, pmap_j, x.bs.sA, x.bs.sRhs, x.bs.sDblk, x.bs.sPmap);
         LU_LAUNCH_CHECK(x);
     }
     if (j + w < x.N && !l21_done) {
@@ -1519,6 +1543,95 @@ static void lu_rec(LuCtx& x, int64_t j0, int w) {
     lu_rec(x, j0 + h, w - h);
 }
 
+// The interchanges of the panels of the outer block at J, applied to the columns [c_lo, c_hi) that the panel-time launches
+// skipped (look-ahead).
+static void lu_permute_deferred(LuCtx& x, int64_t J, int w, int64_t c_lo, int64_t c_hi) {
+    if (c_lo >= c_hi) return;
+    const int npan = (w + LU_NB - 1) / LU_NB, wlast = w - (npan - 1) * LU_NB;
+    const int nct = (int)cdiv64(c_hi - c_lo, PERM_COLS);
+    bhs_prof_begin(BHS_PROF_LU_PANEL, x.st);
+    lu_permute_kernel<<<dim3((unsigned)nct, 1, x.nbatch), 256, 0, x.st>>>(x.A, x.ld, c_lo, c_hi - c_lo, nct, nullptr, 0, J, npan, wlast,
+                                                                          nullptr, x.pmaps + (J / LU_NB) * LU_PMAP, x.bs.sA, 0,
+                                                                          x.bs.sDblk, x.bs.sPmap);
+    bhs_prof_end(BHS_PROF_LU_PANEL, 0.0, x.st);
+    LU_LAUNCH_CHECK(x);
+}
+
+static void lu_rhs_forward(LuCtx& x, int64_t J, int w) {
+    // forward substitution of this block row: y_J = L11^{-1} rhs_J ; rhs_below -= L21 y_J
+    bhs_prof_begin(BHS_PROF_LU_RHS, x.st);
+    rhs_block_solve_kernel<<<dim3(1, 1, x.nbatch), 128, RS_SMEM, x.st>>>(x.A, x.ld, J, w, 0, x.rhs, x.nrhs, x.bs.sA, x.bs.sRhs);
+    LU_LAUNCH_CHECK(x);
+    if (J + w < x.N) {
+        rhs_gemv_sub_kernel<<<dim3((unsigned)cdiv64(x.N - J - w, 8), 1, x.nbatch), 256, 0, x.st>>>(
+            x.A, x.ld, J + w, x.N, J, w, x.rhs, x.nrhs, x.bs.sA, x.bs.sRhs);
+        LU_LAUNCH_CHECK(x);
+    }
+    bhs_prof_end(BHS_PROF_LU_RHS, 0.0, x.st);
+}
+
+// Panel stream of the look-ahead (one per host thread and device; forked from / joined to the caller's stream with events, so
+// the whole factorisation can still be captured into a CUDA graph).  It has the HIGHEST priority: the trailing update on the
+// caller's stream fills every SM with tensor-core CTAs, and the latency-bound panel kernels (a 16-CTA cluster that needs whole
+// SMs) must get the slots those free first, or they would simply queue behind the update.
+static cudaStream_t lu_panel_stream() {
+    thread_local cudaStream_t pool[64] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!pool[dev]) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi = numerically smallest = greatest priority
+        if (cudaStreamCreateWithPriority(&pool[dev], cudaStreamNonBlocking, hi) != cudaSuccess) pool[dev] = nullptr;
+    }
+    return pool[dev];
+}
+
+// Look-ahead (a lone system: nothing else keeps the device busy during the latency-bound panels).  The panel stream
+// factorises the outer block columns one after the other -- panels, the updates inside the block, the forward substitution
+// of the right-hand sides -- and touches nothing outside the current block column.  The caller's stream does everything else
+// of block J once its panels are done: the deferred row interchanges left and right of the block column, the U12 solve, the
+// update of the NEXT block column (after which the panel stream may start on it) and then the rest of the trailing matrix,
+// which thus overlaps the panels of block J + 1.
+static int lu_factor_lookahead(LuCtx& x, cudaStream_t pst) {
+    const cudaStream_t ust = x.st;
+    cudaEvent_t e_panel = nullptr, e_next = nullptr;
+    if (cudaEventCreateWithFlags(&e_panel, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e_next, cudaEventDisableTiming) != cudaSuccess)
+        return BHS_ERR_ALLOC;
+    cudaEventRecord(e_next, ust);  // fork: the panel stream starts behind the work queued ahead of this call
+    cudaStreamWaitEvent(pst, e_next, 0);
+    int64_t last_J = 0;
+    int last_w = 0;
+    for (int64_t J = 0; J < x.N; J += LU_NBO) {
+        const int w = (int)((x.N - J < LU_NBO) ? (x.N - J) : LU_NBO);
+        x.J = J;
+        x.st = pst;
+        lu_rec(x, J, w);
+        if (x.rhs) lu_rhs_forward(x, J, w);
+        last_J = J;
+        last_w = w;
+        cudaEventRecord(e_panel, pst);
+        x.st = ust;
+        cudaStreamWaitEvent(ust, e_panel, 0);  // (after the last block this is the join)
+        if (J + w < x.N) {
+            lu_permute_deferred(x, J, w, 0, J);
+            lu_permute_deferred(x, J, w, J + w, x.N);
+            lu_trsm(x, J, w, J + w, x.N);
+            const int64_t nc_hi = (J + w + LU_NBO < x.N) ? J + w + LU_NBO : x.N;
+            lu_gemm(x, J + w, x.N, J + w, nc_hi, J, w);  // the next block column first
+            cudaEventRecord(e_next, ust);
+            cudaStreamWaitEvent(pst, e_next, 0);
+            lu_gemm(x, J + w, x.N, nc_hi, x.N, J, w);    // the rest overlaps the panels of the next block
+        }
+    }
+    // the interchanges of the last block's panels on the columns left of it
+    x.st = ust;
+    lu_permute_deferred(x, last_J, last_w, 0, last_J);
+    cudaEventDestroy(e_panel);
+    cudaEventDestroy(e_next);
+    return x.err;
+}
+
 static int lu_factor(LuCtx& x) {
     cudaMemsetAsync(x.info, 0, sizeof(int32_t) * x.nbatch, x.st);
     cudaFuncSetAttribute(zgemm_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
@@ -1526,6 +1639,16 @@ static int lu_factor(LuCtx& x) {
     // BHS_LU_GEMM_ONLY=1 (measurement aid, wrong results): issue only the trailing updates, to see how much of a
     // sweep's time the DMMA kernel accounts for on its own
     static const bool gemm_only = getenv("BHS_LU_GEMM_ONLY") != nullptr;
+    // BHS_LU_LOOKAHEAD=0 disables the two-stream look-ahead of lone systems, =2 also uses it for systems in lock step
+    static const int la_mode = [] { const char* e = getenv("BHS_LU_LOOKAHEAD"); return e ? atoi(e) : 1; }();
+    x.lookahead = false;
+    if (!gemm_only && x.tma && la_mode && (x.nbatch == 1 || la_mode >= 2) && x.N > 2 * LU_NBO) {
+        cudaStream_t pst = lu_panel_stream();
+        if (pst) {
+            x.lookahead = true;
+            return lu_factor_lookahead(x, pst);
+        }
+    }
     for (int64_t J = 0; J < x.N; J += LU_NBO) {
         int w = (int)((x.N - J < LU_NBO) ? (x.N - J) : LU_NBO);
         x.J = J;
@@ -1537,18 +1660,7 @@ static int lu_factor(LuCtx& x) {
             continue;
         }
         lu_rec(x, J, w);
-        if (x.rhs) {
-            // forward substitution of this block row: y_J = L11^{-1} rhs_J ; rhs_below -= L21 y_J
-            bhs_prof_begin(BHS_PROF_LU_RHS, x.st);
-            rhs_block_solve_kernel<<<dim3(1, 1, x.nbatch), 128, RS_SMEM, x.st>>>(x.A, x.ld, J, w, 0, x.rhs, x.nrhs, x.bs.sA, x.bs.sRhs);
-            LU_LAUNCH_CHECK(x);
-            if (J + w < x.N) {
-                rhs_gemv_sub_kernel<<<dim3((unsigned)cdiv64(x.N - J - w, 8), 1, x.nbatch), 256, 0, x.st>>>(
-                    x.A, x.ld, J + w, x.N, J, w, x.rhs, x.nrhs, x.bs.sA, x.bs.sRhs);
-                LU_LAUNCH_CHECK(x);
-            }
-            bhs_prof_end(BHS_PROF_LU_RHS, 0.0, x.st);
-        }
+        if (x.rhs) lu_rhs_forward(x, J, w);
         if (J + w < x.N) {
             lu_trsm(x, J, w, J + w, x.N);
             lu_gemm(x, J + w, x.N, J + w, x.N, J, w);
@@ -1593,7 +1705,8 @@ static int lu_setup(LuCtx& x, int64_t N, double* d_A, int64_t ld, double* d_rhs,
     LuWork w = lu_carve(N, nbatch, d_work);
     x.nbatch = nbatch;
     x.bs.sA = strideA; x.bs.sRhs = stride_rhs; x.bs.sIpiv = N; x.bs.sCand = w.ncand;
-    x.bs.sDblk = (int64_t)LU_DBLK; x.bs.sLp = w.sLp; x.bs.sUp = w.sUp;
+    x.bs.sDblk = (int64_t)LU_DBLK; x.bs.sPmap = w.sPmap; x.bs.sLp = w.sLp; x.bs.sUp = w.sUp;
+    x.pmaps = w.pmaps;
     x.A = (cplx*)d_A; x.ld = ld; x.N = N; x.rhs = (cplx*)d_rhs; x.nrhs = nrhs;
     x.ipiv = d_ipiv; x.info = d_info; x.cand[0] = w.cand0; x.cand[1] = w.cand1; x.dblk = w.dblk;
     x.Lp = w.Lp; x.Up = w.Up; x.nks_total = LU_NBO / G_KC; x.J = 0;
