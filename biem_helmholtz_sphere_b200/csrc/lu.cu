@@ -1639,10 +1639,13 @@ static int lu_factor(LuCtx& x) {
     // BHS_LU_GEMM_ONLY=1 (measurement aid, wrong results): issue only the trailing updates, to see how much of a
     // sweep's time the DMMA kernel accounts for on its own
     static const bool gemm_only = getenv("BHS_LU_GEMM_ONLY") != nullptr;
-    // BHS_LU_LOOKAHEAD=0 disables the two-stream look-ahead of lone systems, =2 also uses it for systems in lock step
+    // BHS_LU_LOOKAHEAD=0 disables the two-stream look-ahead of lone systems, =2 also uses it for systems in lock step and for
+    // any size.  By default it serves 256 < N <= 12288: the panels cost O(N^2) and the update O(N^3), so beyond that there is
+    // little left to hide, while the high-priority panel kernels (clusters that need whole SMs) disturb the update -- measured
+    // at N = 36 864: 4.46 s without, 4.81 s with look-ahead; at N = 8192: 86 ms without, 69 ms with.
     static const int la_mode = [] { const char* e = getenv("BHS_LU_LOOKAHEAD"); return e ? atoi(e) : 1; }();
     x.lookahead = false;
-    if (!gemm_only && x.tma && la_mode && (x.nbatch == 1 || la_mode >= 2) && x.N > 2 * LU_NBO) {
+    if (!gemm_only && x.tma && la_mode && (la_mode >= 2 || (x.nbatch == 1 && x.N <= 12288)) && x.N > 2 * LU_NBO) {
         cudaStream_t pst = lu_panel_stream();
         if (pst) {
             x.lookahead = true;
