@@ -424,8 +424,13 @@ def run_b200(args) -> None:
         gi = prof["lu_gemm_inner"]
         am = prof["asm_main"]
         out["roofline"] = {
-            "bound": "tensor", "kernel": "zgemm_tma_kernel (LU trailing update, FP64 DMMA, operands by tensor-map TMA)",
+            "bound": "tensor", "kernel": "zgemm3m_tma_kernel (LU trailing update, FP64 DMMA, operands by tensor-map TMA, three real "
+                                         "products per complex one)",
             "achieved": gemm_tf, "peak": peak_dmma, "unit": "TFLOP/s", "frac": gemm_tf / peak_dmma,
+            "executed_tflops": 0.75 * gemm_tf, "executed_frac": 0.75 * gemm_tf / peak_dmma,
+            "flop_convention": "achieved / frac count the ALGORITHMIC flops of SURVEY 8d (8 real flops per complex multiply-add, "
+                               "(8/3) N^3 per factorisation); the kernel uses the 3M scheme (T1 = Ar Br, T2 = Ai Bi, T3 = (Ar+Ai)(Br+Bi)) "
+                               "and EXECUTES 6, so the tensor pipe itself is busy at executed_frac",
             "peak_source": "FP64 mma.sync m8n8k4 register-resident loop measured in this run (bhs_fp64_peak); "
                            "MEASURED_PEAKS.json carries no FP64 figure; cuBLAS ZGEMM 8192^3 in this run: "
                            f"{peaks['cublas_zgemm_8192']:.2f} TFLOP/s",

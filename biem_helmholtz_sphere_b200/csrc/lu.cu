@@ -356,6 +356,145 @@ __global__ void __launch_bounds__(G_THREADS, MINB)
 }
 static const size_t T_SMEM = (size_t)T_STAGES * 2 * T_STAGE_BYTES + 1024;
 
+// =====================================================================================================
+// The same update with THREE real products per complex one ("3M", the ZGEMM3M scheme of the BLAS):
+//     T1 = Ar Br,  T2 = Ai Bi,  T3 = (Ar + Ai)(Br + Bi);     Re(AB) = T1 - T2,   Im(AB) = T3 - T1 - T2
+// i.e. 6 instead of 8 real flops per complex multiply-add on the tensor cores: a quarter of the DMMA work of the real
+// embedding above is gone.  The price is the usual one of 3M: the imaginary part is formed by cancellation, so its error is
+// bounded normwise (by eps (|Ar| + |Ai|)(|Br| + |Bi|)), not componentwise; LU with partial pivoting only needs the normwise
+// bound (measured: residuals and densities unchanged at the 1e-15 level, tests/test_gpu_kernels.py).
+// Operands exactly as above (tensor-map TMA straight from the matrices, 8 complex k per stage, 128-byte swizzle), CTA tile
+// 64 x 32, four warps of 32 x 16, three resident CTAs per SM.  A k-step contracts the four complex k of one parity of the
+// stage (k = 2 (lane & 3) + p: the pairing that keeps the 16-byte fragment loads conflict-free under the swizzle); every
+// fragment load brings (re, im) of one element and the third operand is one DADD away.
+// C folds into the accumulators at load time: T2 <- Cr, T3 <- Cr - Ci, T1 <- 0 give  C - AB = (T2 - T1, T1 + T2 - T3).
+#define M3_TN 32
+#define M3_STAGES 5
+#define M3_A_BYTES 8192
+#define M3_B_BYTES 4096
+__global__ void __launch_bounds__(G_THREADS, 3)
+    zgemm3m_tma_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__ CUtensorMap mapU, TmaGemmArgs g) {
+    extern __shared__ unsigned char smem_dyn[];
+    __shared__ __align__(8) uint64_t full[M3_STAGES];
+    __shared__ __align__(8) uint64_t empty[M3_STAGES];
+    unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    unsigned char* smA = smem;
+    unsigned char* smB = smem + M3_STAGES * M3_A_BYTES;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 1, wn = warp & 1;
+    const int rt = g.rt0 + blockIdx.y, ct = g.ct0 + blockIdx.x;
+    const int z = blockIdx.z;
+    g.C += (int64_t)z * g.sC;
+    const int trow = (int)(g.row_base + (int64_t)rt * G_TM);
+    const int tcol = (int)(g.col_base + (int64_t)ct * M3_TN);
+    // five box loads per stage (L, four groups of 8 columns of U), shared by the warps' first lanes
+    auto issue = [&](int it, int s, int part) {
+        const int kk = g.k0 + it * G_KC;
+        if (part == 0) {
+            mbar_expect_tx(&full[s], M3_A_BYTES + M3_B_BYTES);
+            tma_load_3d(smA + s * M3_A_BYTES, &mapL, 2 * kk, trow, z, &full[s]);
+            tma_load_3d(smB + s * M3_B_BYTES, &mapU, 2 * tcol, kk, z, &full[s]);
+        } else {
+            tma_load_3d(smB + s * M3_B_BYTES + part * 1024, &mapU, 2 * (tcol + 8 * part), kk, z, &full[s]);
+        }
+    };
+    if (tid == 0) {
+        for (int s = 0; s < M3_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 4);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (lane == 0)
+        for (int s = 0; s < M3_STAGES && s < g.nks; ++s) issue(s, s, warp);
+    // accumulators [row block i][column block j][2 adjacent columns]
+    double t1[4][2][2], t2[4][2][2], t3[4][2][2];
+    const int64_t row0 = (int64_t)trow + wm * 32 + (lane >> 2);
+    const int64_t col0 = (int64_t)tcol + wn * 16 + 2 * (lane & 3);
+    const bool interior = (int64_t)trow >= g.row_lo && (int64_t)trow + G_TM <= g.row_hi && (int64_t)tcol >= g.col_lo &&
+                          (int64_t)tcol + M3_TN <= g.col_hi;
+    cplx* const Cw = g.C + row0 * g.ldc + col0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t r = row0 + 8 * i;
+        const bool rv = interior || (r >= g.row_lo && r < g.row_hi);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int64_t c = col0 + 8 * j + e;
+                cplx v = cmake(0.0, 0.0);
+                if (rv && (interior || (c >= g.col_lo && c < g.col_hi))) v = Cw[(int64_t)(8 * i) * g.ldc + 8 * j + e];
+                t1[i][j][e] = 0.0;
+                t2[i][j][e] = v.x;
+                t3[i][j][e] = v.x - v.y;
+            }
+        }
+    }
+    const int rx = lane >> 2, kq = 2 * (lane & 3);
+    const int a_base = (wm * 32 + rx) * 128;
+    const int b_base = wn * 2 * 1024;
+    for (int it = 0; it < g.nks; ++it) {
+        const int s = it % M3_STAGES;
+        mbar_wait(&full[s], (it / M3_STAGES) & 1);
+        const unsigned char* As = smA + s * M3_A_BYTES + a_base;
+        const unsigned char* Bs = smB + s * M3_B_BYTES + b_base;
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const int k = kq + p;  // this lane's complex k inside the stage
+            const int asw = (k ^ rx) << 4, bsw = k * 128 + ((rx ^ k) << 4);
+            double ar[4], ai[4], as[4], br[2], bi[2], bs[2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double2 v = *reinterpret_cast<const double2*>(As + i * 1024 + asw);
+                ar[i] = v.x; ai[i] = v.y; as[i] = v.x + v.y;
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const double2 v = *reinterpret_cast<const double2*>(Bs + j * 1024 + bsw);
+                br[j] = v.x; bi[j] = v.y; bs[j] = v.x + v.y;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    dmma884(t1[i][j][0], t1[i][j][1], ar[i], br[j]);
+                    dmma884(t2[i][j][0], t2[i][j][1], ai[i], bi[j]);
+                    dmma884(t3[i][j][0], t3[i][j][1], as[i], bs[j]);
+                }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(&empty[s]);
+            // refill the stage that everybody left one iteration ago
+            if (it >= 1 && it - 1 + M3_STAGES < g.nks) {
+                const int sp = (it - 1) % M3_STAGES;
+                mbar_wait(&empty[sp], ((it - 1) / M3_STAGES) & 1);
+                issue(it - 1 + M3_STAGES, sp, warp);
+            }
+        }
+    }
+    // C - AB = (Cr + T2 - T1) + i (T1 + T2 - (T3 - Cr + Ci) ...) with the load-time folding: (t2 - t1, t1 + t2 - t3)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t r = row0 + 8 * i;
+        const bool rv = interior || (r >= g.row_lo && r < g.row_hi);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int64_t c = col0 + 8 * j + e;
+                if (rv && (interior || (c >= g.col_lo && c < g.col_hi)))
+                    Cw[(int64_t)(8 * i) * g.ldc + 8 * j + e] =
+                        cmake(t2[i][j][e] - t1[i][j][e], (t1[i][j][e] + t2[i][j][e]) - t3[i][j][e]);
+            }
+        }
+    }
+}
+static const size_t M3_SMEM = (size_t)M3_STAGES * (M3_A_BYTES + M3_B_BYTES) + 1024;
+
+
 static int gemm_minb() {  // resident CTAs per SM the kernel is compiled for (measurement switch)
     static const int v = [] { const char* e = getenv("BHS_GEMM_MINB"); return e ? atoi(e) : 2; }();
     return v;
@@ -372,6 +511,31 @@ static void launch_zgemm_tma(dim3 grid, cudaStream_t st, const CUtensorMap& mL, 
     if (prod) zgemm_tma_kernel<2, true><<<grid, G_THREADS, T_SMEM, st>>>(mL, mU, t);
     else if (gemm_minb() == 3) zgemm_tma_kernel<3, false><<<grid, G_THREADS, T_SMEM, st>>>(mL, mU, t);
     else zgemm_tma_kernel<2, false><<<grid, G_THREADS, T_SMEM, st>>>(mL, mU, t);
+}
+
+// C[r_lo..r_hi, c_lo..c_hi) -= L[rows, k0 .. k0 + 8 nks) U[.., cols] on the tile grid anchored at (row_base, column 0): the 3M
+// kernel (default) or the real-embedding ("4M") kernel (BHS_GEMM_4M=1, the A/B reference)
+static void launch_gemm_window(cudaStream_t st, const CUtensorMap& mL, const CUtensorMap& mU, cplx* C, int64_t ldc, int64_t sC,
+                               int64_t row_base, int64_t r_lo, int64_t r_hi, int64_t c_lo, int64_t c_hi, int k0, int nks,
+                               int nbatch) {
+    static const bool use4m = getenv("BHS_GEMM_4M") != nullptr;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(zgemm3m_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M3_SMEM);
+        attr_set = true;
+    }
+    const int tn = use4m ? G_TN : M3_TN;
+    TmaGemmArgs t;
+    t.C = C; t.ldc = ldc; t.sC = sC;
+    t.row_base = row_base; t.col_base = 0;
+    t.rt0 = (int)((r_lo - row_base) / G_TM);
+    t.ct0 = (int)(c_lo / tn);
+    const int rt1 = (int)((r_hi - 1 - row_base) / G_TM), ct1 = (int)((c_hi - 1) / tn);
+    t.row_lo = r_lo; t.row_hi = r_hi; t.col_lo = c_lo; t.col_hi = c_hi;
+    t.k0 = k0; t.nks = nks;
+    dim3 grid(ct1 - t.ct0 + 1, rt1 - t.rt0 + 1, nbatch);
+    if (use4m) launch_zgemm_tma(grid, st, mL, mU, t);
+    else zgemm3m_tma_kernel<<<grid, G_THREADS, M3_SMEM, st>>>(mL, mU, t);
 }
 
 // ---- tensor maps (driver entry point fetched through the runtime: no link-time dependency on libcuda) -----------------
@@ -1347,18 +1511,9 @@ static void lu_gemm(LuCtx& x, int64_t r_lo, int64_t r_hi, int64_t c_lo, int64_t 
     if (r_lo >= r_hi || c_lo >= c_hi || K <= 0) return;
     const int pcat = (K >= LU_NBO || (k0 == x.J && r_lo >= x.J + LU_NBO)) ? BHS_PROF_LU_GEMM : BHS_PROF_LU_GEMM_IN;
     if (x.tma) {
-        TmaGemmArgs t;
-        t.C = x.A; t.ldc = x.ld;
-        t.row_base = x.J; t.col_base = 0;
-        t.rt0 = (int)((r_lo - x.J) / G_TM);
-        t.ct0 = (int)(c_lo / G_TN);
-        const int rt1 = (int)((r_hi - 1 - x.J) / G_TM), ct1 = (int)((c_hi - 1) / G_TN);
-        t.row_lo = r_lo; t.row_hi = r_hi; t.col_lo = c_lo; t.col_hi = c_hi;
-        t.sC = x.bs.sA;
-        t.k0 = (int)k0; t.nks = (K + G_KC - 1) / G_KC;
-        dim3 grid(ct1 - t.ct0 + 1, rt1 - t.rt0 + 1, x.nbatch);
         bhs_prof_begin(pcat, x.st);
-        launch_zgemm_tma(grid, x.st, x.mapL, x.mapU, t);
+        launch_gemm_window(x.st, x.mapL, x.mapU, x.A, x.ld, x.bs.sA, x.J, r_lo, r_hi, c_lo, c_hi, (int)k0, (K + G_KC - 1) / G_KC,
+                           x.nbatch);
         bhs_prof_end(pcat, 8.0 * (double)(r_hi - r_lo) * (double)(c_hi - c_lo) * (double)K * x.nbatch, x.st);
         LU_LAUNCH_CHECK(x);
         return;
@@ -1798,11 +1953,7 @@ extern "C" int bhs_zgemm_sub(int64_t M, int64_t N, int64_t K, const double* d_A,
         int rc = make_operand_map(&mL, d_A, M, K, lda, 1, 0, G_TM);
         if (rc == BHS_OK) rc = make_operand_map(&mU, d_B, K, N, ldb, 1, 0, G_KC);
         if (rc != BHS_OK) return rc;
-        TmaGemmArgs t;
-        t.C = (cplx*)d_C; t.ldc = ldc; t.row_base = 0; t.col_base = 0; t.rt0 = 0; t.ct0 = 0;
-        t.row_lo = 0; t.row_hi = M; t.col_lo = 0; t.col_hi = N; t.sC = 0; t.k0 = 0; t.nks = (int)nks;
-        dim3 grid((unsigned)cdiv64(N, G_TN), (unsigned)cdiv64(M, G_TM));
-        launch_zgemm_tma(grid, st, mL, mU, t);
+        launch_gemm_window(st, mL, mU, (cplx*)d_C, ldc, 0, 0, 0, M, 0, N, 0, (int)nks, 1);
         BHS_CHECK_LAUNCH();
         return BHS_OK;
     }
