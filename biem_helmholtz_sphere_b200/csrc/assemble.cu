@@ -277,6 +277,8 @@ struct AsmArgs {
     const int32_t* deg2;
     const cplx* Y2;    // [B*B][H2]
     const cplx* hp;    // [nsys][B*B][L2]
+    const cplx* Su;    // [nsys][ucap][H2]  S vectors of the distinct translations (register-resident kernel only)
+    int ucap;
     const cplx* rowf;  // [nsys][B][H]
     const cplx* colf;
     const cplx* diag;
@@ -405,6 +407,262 @@ __global__ void __launch_bounds__(ASM_THREADS) assemble_kernel(AsmArgs a) {
     }
 }
 
+// ---- the assembly kernel, register-resident form ------------------------------------------------------------
+// Used whenever a tile has at most 32 term layers and two S windows fit in shared memory (every 3-D plan up to
+// n_end = 32, small 2-D plans).  Same arithmetic, term order and roundings as assemble_kernel above (bit-identical
+// matrices), different data movement:
+//   * each thread keeps the coefficients and S indices of ITS tile entry in registers for the whole CTA lifetime
+//     (NT doubles + NT/2 packed index words), loaded once with coalesced global loads: the contraction issues one
+//     shared-memory load per term instead of three, and shared memory only holds S windows;
+//   * the S vectors of the distinct translations are built once by s_vectors_kernel; a CTA streams the windows of its
+//     translations through a two-stage TMA ring, two translations ahead of the contraction;
+//   * the member list of the NEXT translation is fetched into shared memory while the current one is written, so the
+//     write phase is  LDS -> factor loads (L1) -> stores  with no chain of dependent global loads in front of it;
+//   * the diagonal blocks are written by the same CTAs (no separate launch).
+#define ASM_MEMCAP 256  // members of one translation held in shared memory (more: read from global)
+
+__global__ void s_vectors_kernel(int H2, int L2, int64_t np, int ucap, const int32_t* __restrict__ n_unique,
+                                 const int32_t* __restrict__ grp_rep, const int32_t* __restrict__ deg2,
+                                 const cplx* __restrict__ Y2, const cplx* __restrict__ hp, cplx* __restrict__ Su) {
+    const int U = n_unique[0], sys = blockIdx.z;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= H2) return;
+    const int dg = deg2[j];
+    for (int u = blockIdx.y; u < U; u += gridDim.y) {
+        const int64_t pr = grp_rep[u];
+        Su[((int64_t)sys * ucap + u) * H2 + j] = cmul(Y2[pr * H2 + j], hp[((int64_t)sys * np + pr) * L2 + dg]);
+    }
+}
+
+// One member pair of a translation, decoded once per CTA into the three offsets the write phase adds to its
+// thread-constant bases.  (rs, cs): strides of the row / column factor tables in BYTES per ball -- H * 16 when the factors
+// are read from global memory, TILE_R * 16 / TILE_C * 16 when the tile's factors are staged in shared memory.
+struct __align__(16) AsmMember {
+    int32_t row_off;  // b * rs   (-1: row ball outside the strip of this call, or padding)
+    int32_t col_off;  // b' * cs
+    int64_t out_off;  // (b - b_lo) * H * ld + b' * H   (elements)
+};
+__device__ __forceinline__ AsmMember asm_member(int pk, int H, int rs, int cs, int b_lo, int b_hi, int64_t hld) {
+    const int b = pk >> 16, bq = pk & 0xffff;
+    AsmMember m;
+    m.row_off = (b >= b_lo && b < b_hi) ? b * rs : -1;
+    m.col_off = bq * cs;
+    m.out_off = (int64_t)(b - b_lo) * hld + (int64_t)bq * H;
+    return m;
+}
+// keeps a computed shared-window address in a register (ptxas otherwise re-derives it from %cta-id / %tid at every use
+// when registers are tight: ~15 instructions per use)
+__device__ __forceinline__ uint32_t pin_u32(uint32_t v) {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
+__device__ __forceinline__ cplx lds_cplx(uint32_t addr) {
+    cplx v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ AsmMember lds_member(uint32_t addr) {
+    AsmMember m;
+    int32_t lo, hi;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(m.row_off), "=r"(m.col_off), "=r"(lo), "=r"(hi) : "r"(addr));
+    m.out_off = (int64_t)(((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo);
+    return m;
+}
+
+// FSM: the row / column factors of this tile position (B x 4 and B x 64 values) are staged in shared memory once per CTA,
+// so the write phase has no global load at all (taken when they fit: B <= ASM_FSM_MAXB)
+#define ASM_FSM_MAXB 36
+template <int NT, bool FSM>
+__global__ void __launch_bounds__(ASM_THREADS, 2) assemble_reg_kernel(AsmArgs a, int stage_bytes) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full[2];
+    __shared__ AsmMember s_mem[2][ASM_MEMCAP];
+    const int tid = threadIdx.x;
+    const bhs_tile_hdr hd = a.tiles[blockIdx.x];
+    const int tiles_c = (a.H + BHS_TILE_C - 1) / BHS_TILE_C;
+    const int tr = blockIdx.x / tiles_c, tc = blockIdx.x % tiles_c;
+    const int sys = blockIdx.z;
+    const int nt = hd.nt;
+    const int h = tr * BHS_TILE_R + tid / BHS_TILE_C, hp = tc * BHS_TILE_C + tid % BHS_TILE_C;
+    const bool ok = h < a.H && hp < a.H;
+    const int U = a.n_unique[0];
+    const int ustep = gridDim.y;
+    const int64_t hld = (int64_t)a.H * a.ld;
+    const uint32_t win_bytes = (uint32_t)hd.sy_cnt * (uint32_t)sizeof(cplx);
+    const cplx* su = a.Su + (int64_t)sys * a.ucap * a.H2 + hd.sy_lo;
+    const uint32_t sa_stage = pin_u32(smem_u32(smem_raw));  // shared-window addresses: S stages, member lists, staged factors
+    const uint32_t sa_mem = pin_u32(smem_u32(&s_mem[0][0]));
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        mbar_fence_init();
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const int u = blockIdx.y + s * ustep;
+            if (u < U) {
+                mbar_expect_tx(&full[s], win_bytes);
+                tma_load_1d(smem_raw + (size_t)s * stage_bytes, su + (int64_t)u * a.H2, win_bytes, &full[s]);
+            }
+        }
+    }
+    // member range of the first translation, and (below) its members
+    int q0 = 0, cnt = 0;
+    if ((int)blockIdx.y < U) {
+        q0 = __ldg(a.grp_start + blockIdx.y);
+        cnt = __ldg(a.grp_start + blockIdx.y + 1) - q0;
+    }
+    // this thread's tile entry: coefficients and packed S indices of every term layer
+    double cf_[NT];
+    uint32_t ix_[NT / 2];
+    {
+        const double* cp = a.coef + hd.coef_off + tid;
+        const uint16_t* ip = a.cidx + hd.idx_off + tid;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) cf_[t] = (t < nt) ? __ldg(cp + t * BHS_TILE_E) : 0.0;
+#pragma unroll
+        for (int t = 0; t < NT; t += 2) {
+            const uint32_t lo = (t < nt) ? __ldg(ip + t * BHS_TILE_E) : 0u;
+            const uint32_t hi = (t + 1 < nt) ? __ldg(ip + (t + 1) * BHS_TILE_E) : 0u;
+            ix_[t / 2] = (lo | (hi << 16)) * (uint32_t)sizeof(cplx);  // byte offsets (windows are < 4096 entries)
+        }
+    }
+    // thread-constant bases: everything a member adds is one of its three precomputed offsets
+    const unsigned char* rowf_h = reinterpret_cast<const unsigned char*>(a.rowf + (int64_t)sys * a.B * a.H + h);
+    const unsigned char* colf_hp = reinterpret_cast<const unsigned char*>(a.colf + (int64_t)sys * a.B * a.H + hp);
+    const int rs = (FSM ? BHS_TILE_R : a.H) * (int)sizeof(cplx), cs = (FSM ? BHS_TILE_C : a.H) * (int)sizeof(cplx);
+    uint32_t sa_rowf = 0, sa_colf = 0;
+    if (FSM) {
+        cplx* s_rowf = reinterpret_cast<cplx*>(smem_raw + (size_t)2 * stage_bytes);
+        cplx* s_colf = s_rowf + (size_t)a.B * BHS_TILE_R;
+        const cplx* gr = a.rowf + (int64_t)sys * a.B * a.H + tr * BHS_TILE_R;
+        const cplx* gc = a.colf + (int64_t)sys * a.B * a.H + tc * BHS_TILE_C;
+        for (int e = tid; e < a.B * BHS_TILE_R; e += ASM_THREADS) {
+            const int b = e / BHS_TILE_R, r = e % BHS_TILE_R;
+            s_rowf[e] = (tr * BHS_TILE_R + r < a.H) ? __ldg(gr + (int64_t)b * a.H + r) : cmake(0.0, 0.0);
+        }
+        for (int e = tid; e < a.B * BHS_TILE_C; e += ASM_THREADS) {
+            const int b = e / BHS_TILE_C, c = e % BHS_TILE_C;
+            s_colf[e] = (tc * BHS_TILE_C + c < a.H) ? __ldg(gc + (int64_t)b * a.H + c) : cmake(0.0, 0.0);
+        }
+        sa_rowf = pin_u32(smem_u32(s_rowf + tid / BHS_TILE_C));
+        sa_colf = pin_u32(smem_u32(s_colf + tid % BHS_TILE_C));
+    }
+    cplx* out_base = a.A + (int64_t)sys * a.sys_stride + (int64_t)h * a.ld + hp;
+    // diagonal blocks of this tile position: balls b_lo + y, b_lo + y + gridDim.y, ...
+    if (ok) {
+        const cplx* dg = a.diag + (int64_t)sys * a.B * a.H + h;
+        for (int b = a.b_lo + blockIdx.y; b < a.b_hi; b += ustep) {
+            cplx v = cmake(0.0, 0.0);
+            if (h == hp) v = __ldg(dg + (int64_t)b * a.H);
+            out_base[(int64_t)(b - a.b_lo) * hld + (int64_t)b * a.H] = v;
+        }
+    }
+    // member lists live in shared memory padded to a multiple of four with inactive entries (row_off = -1); the rare
+    // members beyond ASM_MEMCAP (more spheres than that sharing one translation) are written by the tail loop below
+    auto stage_members = [&](int buf, int q_first, int n) {
+        const int n4 = min((n + 3) & ~3, ASM_MEMCAP);
+        if (tid < n4) {
+            AsmMember m;
+            m.row_off = -1; m.col_off = 0; m.out_off = 0;
+            if (tid < n) m = asm_member(__ldg(a.members + q_first + tid), a.H, rs, cs, a.b_lo, a.b_hi, hld);
+            s_mem[buf][tid] = m;
+        }
+    };
+    stage_members(0, q0, cnt);
+    __syncthreads();  // barrier inits, staged factors and s_mem[0] visible
+
+    int it = 0;
+    for (int u = blockIdx.y; u < U; u += ustep, ++it) {
+        const int st = it & 1;
+        // member range of the next translation (consumed after the contraction)
+        const int un = u + ustep;
+        int q0n = 0, cntn = 0;
+        if (un < U) {
+            q0n = __ldg(a.grp_start + un);
+            cntn = __ldg(a.grp_start + un + 1) - q0n;
+        }
+        mbar_wait(&full[st], (uint32_t)((it >> 1) & 1));
+        const uint32_t sa_sy = sa_stage + (uint32_t)st * (uint32_t)stage_bytes;
+        double ar = 0.0, ai = 0.0;
+        // four layers per (CTA-uniform) branch: their loads are issued together; a padded layer reads entry 0 of the
+        // window and its FMAs are skipped, so the sums are those of the layer-by-layer loop
+#pragma unroll
+        for (int t0 = 0; t0 < NT; t0 += 4) {
+            if (t0 < nt) {
+                cplx sv[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int t = t0 + i;
+                    const uint32_t ix = (t & 1) ? (ix_[t / 2] >> 16) : (ix_[t / 2] & 0xffffu);
+                    sv[i] = lds_cplx(sa_sy + ix);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const bool on = t0 + i < nt;
+                    ar = on ? fma(cf_[t0 + i], sv[i].x, ar) : ar;
+                    ai = on ? fma(cf_[t0 + i], sv[i].y, ai) : ai;
+                }
+            }
+        }
+        stage_members(st ^ 1, q0n, cntn);
+        __syncthreads();  // everyone is done with stage st (refill it) and with s_mem[st ^ 1] of the previous translation
+        if (tid == 0) {
+            const int u2 = u + 2 * ustep;
+            if (u2 < U) {
+                mbar_expect_tx(&full[st], win_bytes);
+                tma_load_1d(smem_raw + (size_t)st * stage_bytes, su + (int64_t)u2 * a.H2, win_bytes, &full[st]);
+            }
+        }
+        // write phase: every pair that shares this translation, four at a time, factor loads ahead of the stores
+        if (ok) {
+            const cplx v = cmake(ar, ai);
+            const int n4 = min((cnt + 3) & ~3, ASM_MEMCAP);
+            uint32_t sa_m = sa_mem + (uint32_t)st * (uint32_t)(ASM_MEMCAP * sizeof(AsmMember));
+            for (int m0 = 0; m0 < n4; m0 += 4, sa_m += 4 * (uint32_t)sizeof(AsmMember)) {
+                AsmMember mm[4];
+                cplx rf[4], cf[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) mm[i] = lds_member(sa_m + i * (uint32_t)sizeof(AsmMember));
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (mm[i].row_off >= 0) {
+                        rf[i] = FSM ? lds_cplx(sa_rowf + mm[i].row_off) : __ldg(reinterpret_cast<const cplx*>(rowf_h + mm[i].row_off));
+                        cf[i] = FSM ? lds_cplx(sa_colf + mm[i].col_off) : __ldg(reinterpret_cast<const cplx*>(colf_hp + mm[i].col_off));
+                    }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (mm[i].row_off >= 0) out_base[mm[i].out_off] = cmul(cmul(v, rf[i]), cf[i]);
+            }
+            for (int m = ASM_MEMCAP; m < cnt; ++m) {  // overflow of the shared-memory member list
+                const AsmMember mo = asm_member(__ldg(a.members + q0 + m), a.H, a.H * (int)sizeof(cplx), a.H * (int)sizeof(cplx),
+                                                a.b_lo, a.b_hi, hld);
+                if (mo.row_off >= 0)
+                    out_base[mo.out_off] = cmul(cmul(v, __ldg(reinterpret_cast<const cplx*>(rowf_h + mo.row_off))),
+                                                __ldg(reinterpret_cast<const cplx*>(colf_hp + mo.col_off)));
+            }
+        }
+        q0 = q0n;
+        cnt = cntn;
+    }
+}
+
+// Which plans / problem sizes take the register-resident kernel; the S-vector scratch it needs (bytes, 0 if not taken).
+static bool asm_reg_shape(const bhs_plan* p, int B, int nsys, int* stage_bytes, int64_t* su_bytes) {
+    const int64_t np = (int64_t)B * B;
+    const int64_t ucap = np - B;
+    const int sb = (int)((((int64_t)p->max_sy_cnt * (int64_t)sizeof(cplx)) + 127) & ~(int64_t)127);
+    const int64_t sub = (int64_t)nsys * ucap * p->H2 * (int64_t)sizeof(cplx);
+    if (stage_bytes) *stage_bytes = sb;
+    if (su_bytes) *su_bytes = 0;
+    static const bool legacy = getenv("BHS_ASM_LEGACY") != nullptr;  // A/B switch: the shared-memory-resident kernel
+    if (legacy || B < 2 || p->max_nt > 32 || (int64_t)p->max_sy_cnt * (int64_t)sizeof(cplx) > 48 * 1024 ||
+        sub > ((int64_t)1 << 30))
+        return false;
+    if (su_bytes) *su_bytes = sub;
+    return true;
+}
+
 // ---- host entries -------------------------------------------------------------------------------------------
 static inline int64_t al256(int64_t v) { return (v + 255) & ~(int64_t)255; }
 
@@ -418,6 +676,7 @@ struct AsmWork {
     cplx* colf;
     cplx* diag;
     int32_t *rep, *uid, *cursor, *n_unique, *grp_rep, *grp_start, *members;
+    cplx* Su;         // S vectors of the distinct translations (register-resident kernel), else null
     double* scratch;  // global order-sequence scratch of the radial kernels (very high orders only), else null
     int64_t bytes;
 };
@@ -450,6 +709,10 @@ static AsmWork carve(const bhs_plan* p, int B, int nsys, void* base) {
     w.grp_rep = (int32_t*)take(np * 4);
     w.grp_start = (int32_t*)take((np + 1) * 4);
     w.members = (int32_t*)take(np * 4);
+    {
+        int64_t su_bytes = 0;
+        w.Su = asm_reg_shape(p, B, nsys, nullptr, &su_bytes) ? (cplx*)take(su_bytes) : nullptr;
+    }
     {
         int n_store, T;
         size_t smem;
@@ -561,6 +824,51 @@ static int assemble_impl(const bhs_plan_t* plan, int B, int nsys, const double* 
     a.tiles = plan->d_tiles; a.coef = plan->d_coef; a.cidx = plan->d_cidx; a.deg2 = plan->d_deg2;
     a.Y2 = w.Y2; a.hp = w.hp; a.rowf = w.rowf; a.colf = w.colf; a.diag = w.diag;
     a.A = (cplx*)d_A; a.ld = ld; a.sys_stride = sys_stride;
+    a.Su = w.Su; a.ucap = (int)(np - B);
+    const int ntiles = plan->tiles_r * plan->tiles_c;
+    if (nsys > 65535) return BHS_ERR_UNSUPPORTED;
+    int stage_bytes = 0;
+    if (asm_reg_shape(plan, B, nsys, &stage_bytes, nullptr)) {
+        // register-resident kernel: S vectors of the distinct translations first (U is only known on the device: the
+        // y-dimension strides over them)
+        {
+            int64_t gy = np - B < 1024 ? np - B : 1024;
+            dim3 sgrid((unsigned)((plan->H2 + 127) / 128), (unsigned)gy, (unsigned)nsys);
+            s_vectors_kernel<<<sgrid, 128, 0, st>>>(plan->H2, plan->L2, np, a.ucap, w.n_unique, w.grp_rep, plan->d_deg2, w.Y2,
+                                                   w.hp, w.Su);
+            BHS_CHECK_LAUNCH();
+        }
+        bhs_prof_end(BHS_PROF_ASM_PRE, 0.0, st);
+        bhs_prof_begin(BHS_PROF_ASM_MAIN, st);
+        // about six waves of CTAs (two resident per SM): every CTA first loads its tile into registers (and stages its
+        // factors), so longer CTAs amortise that better, shorter ones balance the last wave better
+        int64_t chunks = (6 * 2 * bhs_sm_count() + (int64_t)ntiles * nsys - 1) / ((int64_t)ntiles * nsys);
+        if (chunks < 1) chunks = 1;
+        if (chunks > np - B) chunks = np - B;
+        if (chunks > 65535) chunks = 65535;
+        dim3 grid((unsigned)ntiles, (unsigned)chunks, (unsigned)nsys);
+        const bool fsm = B <= ASM_FSM_MAXB;
+        const size_t smem = (size_t)2 * stage_bytes + (fsm ? (size_t)B * (BHS_TILE_R + BHS_TILE_C) * sizeof(cplx) : 0);
+        const int nt_max = plan->max_nt;
+#define BHS_ASM_REG_LAUNCH(NT)                                                                                         \
+    do {                                                                                                               \
+        if (fsm) {                                                                                                     \
+            cudaFuncSetAttribute(assemble_reg_kernel<NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+            assemble_reg_kernel<NT, true><<<grid, ASM_THREADS, smem, st>>>(a, stage_bytes);                            \
+        } else {                                                                                                       \
+            cudaFuncSetAttribute(assemble_reg_kernel<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            assemble_reg_kernel<NT, false><<<grid, ASM_THREADS, smem, st>>>(a, stage_bytes);                           \
+        }                                                                                                              \
+    } while (0)
+        if (nt_max <= 8) BHS_ASM_REG_LAUNCH(8);
+        else if (nt_max <= 16) BHS_ASM_REG_LAUNCH(16);
+        else if (nt_max <= 24) BHS_ASM_REG_LAUNCH(24);
+        else BHS_ASM_REG_LAUNCH(32);
+#undef BHS_ASM_REG_LAUNCH
+        BHS_CHECK_LAUNCH();
+        bhs_prof_end(BHS_PROF_ASM_MAIN, 16.0 * (double)(b_hi - b_lo) * plan->H * (double)N * nsys, st);
+        return BHS_OK;
+    }
     // shared-memory budget: SY window (worst case H2 entries) + resident coefficient layers
     const size_t budget = 200 * 1024;
     size_t sy_bytes = ((size_t)plan->max_sy_cnt * sizeof(cplx) + 127) & ~(size_t)127;  // largest window of any tile
@@ -573,13 +881,12 @@ static int assemble_impl(const bhs_plan_t* plan, int B, int nsys, const double* 
     a.nt_res = plan->max_nt < nt_cap ? (plan->max_nt > 0 ? plan->max_nt : 1) : nt_cap;
     size_t smem = (size_t)a.nt_res * (ASM_LAYER_COEF + ASM_LAYER_IDX) + sy_bytes;
     cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const int ntiles = plan->tiles_r * plan->tiles_c;
     // The number of distinct translations U is only known on the device: the y-dimension strides over them, sized
     // for about four waves of CTAs (4 resident per SM) and never more than the off-diagonal pair count.
     int64_t chunks = (4 * 4 * bhs_sm_count() + (int64_t)ntiles * nsys - 1) / ((int64_t)ntiles * nsys);
     if (chunks < 1) chunks = 1;
     if (chunks > np - B) chunks = np - B > 0 ? np - B : 1;
-    if (chunks > 65535 || nsys > 65535) return BHS_ERR_UNSUPPORTED;
+    if (chunks > 65535) return BHS_ERR_UNSUPPORTED;
     dim3 grid((unsigned)ntiles, (unsigned)chunks, (unsigned)nsys);
     bhs_prof_end(BHS_PROF_ASM_PRE, 0.0, st);
     bhs_prof_begin(BHS_PROF_ASM_MAIN, st);
