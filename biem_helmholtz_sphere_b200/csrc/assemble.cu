@@ -43,7 +43,11 @@ __global__ void pair_vectors_kernel(int d, int B, const double* __restrict__ cen
 // same t many times (4x4 grid: 48 distinct t among 240 ordered pairs; 8x8 grid: 224 among 4032), so the
 // contraction is done once per DISTINCT t and the result is scaled and written for every pair that shares it.
 // rep[i] = smallest pair index with bit-identical t (exact comparison: irregular geometries simply get U = np - B).
-__global__ void pair_rep_kernel(int d, int B, int dedupe, const double* __restrict__ tv, int32_t* __restrict__ rep) {
+// pm = 1 (register-resident kernel): pairs with t and -t share a group as well.  Every term of (S|R)_{h',h} has
+// n'' = n + n' (mod 2) and S_{h''}(-t) = (-1)^{n''} S_{h''}(t), so (S|R)_{h',h}(-t) = (-1)^{n+n'} (S|R)_{h',h}(t): the block of
+// (b', b) is the block of (b, b') up to that sign, for ANY geometry (c_b - c_b' and c_b' - c_b are exact negatives).  Members
+// whose translation is the negative of the representative's carry bit 31 in their packed entry.
+__global__ void pair_rep_kernel(int d, int B, int dedupe, int pm, const double* __restrict__ tv, int32_t* __restrict__ rep) {
     extern __shared__ __align__(16) double s_tv[];  // [d][np] when it fits (use_smem), else the scan reads global memory
     const int np = B * B;
     const bool use_smem = dedupe && (size_t)np * d * sizeof(double) <= 96 * 1024;
@@ -55,23 +59,35 @@ __global__ void pair_rep_kernel(int d, int B, int dedupe, const double* __restri
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= np) return;
     if (i / B == i % B) { rep[i] = -1; return; }
-    if (!dedupe) { rep[i] = i; return; }
+    if (!dedupe) {  // no search: only the pair and its transpose share a group
+        const int j = (i % B) * B + i / B;
+        rep[i] = (pm && j < i) ? j : i;
+        return;
+    }
     double t[BHS_MAX_NODES + 2];
     for (int a = 0; a < d; ++a) t[a] = T[(int64_t)a * np + i];
     int r = i;
     for (int j = 0; j < i; ++j) {
-        if (T[j] != t[0]) continue;  // first component differs (the diagonal pairs carry a dummy direction: checked below)
+        // first component differs (the diagonal pairs carry a dummy direction: checked below)
+        const double tj = T[j];
+        const bool eq = tj == t[0], ng = pm && tj == -t[0];
+        if (!eq && !ng) continue;
         if (j / B == j % B) continue;
-        bool same = true;
-        for (int a = 1; a < d; ++a) same = same && (T[(int64_t)a * np + j] == t[a]);
-        if (same) { r = j; break; }
+        bool same = eq, opp = ng;
+        for (int a = 1; a < d; ++a) {
+            const double v = T[(int64_t)a * np + j];
+            same = same && (v == t[a]);
+            opp = opp && (v == -t[a]);
+        }
+        if (same || opp) { r = j; break; }
     }
     rep[i] = r;
 }
 // Single CTA: number the distinct translations and bucket the pairs.
 //   n_unique[0] = U;  grp_rep[u] = representative pair;  grp_start[u..u+1) -> members[] ((b << 16) | b')
 // uid[] and cursor[] are scratch of np ints each.
-__global__ void __launch_bounds__(1024) pair_group_kernel(int B, const int32_t* __restrict__ rep, int32_t* __restrict__ uid,
+__global__ void __launch_bounds__(1024) pair_group_kernel(int B, int d, int pm, const double* __restrict__ tv,
+                                                          const int32_t* __restrict__ rep, int32_t* __restrict__ uid,
                                                           int32_t* __restrict__ cursor, int32_t* __restrict__ n_unique,
                                                           int32_t* __restrict__ grp_rep, int32_t* __restrict__ grp_start,
                                                           int32_t* __restrict__ members) {
@@ -135,8 +151,14 @@ __global__ void __launch_bounds__(1024) pair_group_kernel(int B, const int32_t* 
     // pass 4: fill (order inside a group is irrelevant: every member gets the same block)
     for (int i = tid; i < np; i += T)
         if (rep[i] >= 0) {
-            const int u = uid[rep[i]];
-            members[grp_start[u] + atomicAdd(&cursor[u], 1)] = ((i / B) << 16) | (i % B);  // packed (b, b')
+            const int r = rep[i], u = uid[r];
+            int neg = 0;  // translation of pair i is the negative of its representative's (first nonzero component decides)
+            if (pm)
+                for (int a = 0; a < d; ++a) {
+                    const double ti = tv[(int64_t)a * np + i], tr = tv[(int64_t)a * np + r];
+                    if (ti != tr) { neg = 1; break; }
+                }
+            members[grp_start[u] + atomicAdd(&cursor[u], 1)] = (neg << 31) | ((i / B) << 16) | (i % B);  // packed (b, b')
         }
 }
 
@@ -274,6 +296,7 @@ struct AsmArgs {
     const bhs_tile_hdr* tiles;
     const double* coef;
     const uint16_t* cidx;
+    const int32_t* deg;   // [H]  degree of each harmonic
     const int32_t* deg2;
     const cplx* Y2;    // [B*B][H2]
     const cplx* hp;    // [nsys][B*B][L2]
@@ -439,14 +462,14 @@ __global__ void s_vectors_kernel(int H2, int L2, int64_t np, int ucap, const int
 // are read from global memory, TILE_R * 16 / TILE_C * 16 when the tile's factors are staged in shared memory.
 struct __align__(16) AsmMember {
     int32_t row_off;  // b * rs   (-1: row ball outside the strip of this call, or padding)
-    int32_t col_off;  // b' * cs
+    int32_t col_off;  // b' * cs, bit 31: the member's translation is the NEGATIVE of the group's (block sign (-1)^(n+n'))
     int64_t out_off;  // (b - b_lo) * H * ld + b' * H   (elements)
 };
 __device__ __forceinline__ AsmMember asm_member(int pk, int H, int rs, int cs, int b_lo, int b_hi, int64_t hld) {
-    const int b = pk >> 16, bq = pk & 0xffff;
+    const int b = (pk >> 16) & 0x7fff, bq = pk & 0xffff;
     AsmMember m;
     m.row_off = (b >= b_lo && b < b_hi) ? b * rs : -1;
-    m.col_off = bq * cs;
+    m.col_off = (bq * cs) | (pk & (int)0x80000000);
     m.out_off = (int64_t)(b - b_lo) * hld + (int64_t)bq * H;
     return m;
 }
@@ -459,13 +482,13 @@ __device__ __forceinline__ uint32_t pin_u32(uint32_t v) {
 }
 __device__ __forceinline__ cplx lds_cplx(uint32_t addr) {
     cplx v;
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
     return v;
 }
 __device__ __forceinline__ AsmMember lds_member(uint32_t addr) {
     AsmMember m;
     int32_t lo, hi;
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(m.row_off), "=r"(m.col_off), "=r"(lo), "=r"(hi) : "r"(addr));
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(m.row_off), "=r"(m.col_off), "=r"(lo), "=r"(hi) : "r"(addr) : "memory");
     m.out_off = (int64_t)(((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo);
     return m;
 }
@@ -549,6 +572,8 @@ __global__ void __launch_bounds__(ASM_THREADS, 2) assemble_reg_kernel(AsmArgs a,
         sa_colf = pin_u32(smem_u32(s_colf + tid % BHS_TILE_C));
     }
     cplx* out_base = a.A + (int64_t)sys * a.sys_stride + (int64_t)h * a.ld + hp;
+    // block sign of a member whose translation is the negative of its group's: (-1)^(n + n')
+    const double sflip = (ok && ((__ldg(a.deg + h) + __ldg(a.deg + hp)) & 1)) ? -1.0 : 1.0;
     // diagonal blocks of this tile position: balls b_lo + y, b_lo + y + gridDim.y, ...
     if (ok) {
         const cplx* dg = a.diag + (int64_t)sys * a.B * a.H + h;
@@ -586,7 +611,8 @@ __global__ void __launch_bounds__(ASM_THREADS, 2) assemble_reg_kernel(AsmArgs a,
         const uint32_t sa_sy = sa_stage + (uint32_t)st * (uint32_t)stage_bytes;
         double ar = 0.0, ai = 0.0;
         // four layers per (CTA-uniform) branch: their loads are issued together; a padded layer reads entry 0 of the
-        // window and its FMAs are skipped, so the sums are those of the layer-by-layer loop
+        // window and its FMAs are skipped, so the sums are those of a layer-by-layer loop.  (Issuing the next four loads
+        // ahead of the FMAs was measured slower: the 16 extra registers spill.)
 #pragma unroll
         for (int t0 = 0; t0 < NT; t0 += 4) {
             if (t0 < nt) {
@@ -627,19 +653,25 @@ __global__ void __launch_bounds__(ASM_THREADS, 2) assemble_reg_kernel(AsmArgs a,
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                     if (mm[i].row_off >= 0) {
+                        const int co = mm[i].col_off & 0x7fffffff;
                         rf[i] = FSM ? lds_cplx(sa_rowf + mm[i].row_off) : __ldg(reinterpret_cast<const cplx*>(rowf_h + mm[i].row_off));
-                        cf[i] = FSM ? lds_cplx(sa_colf + mm[i].col_off) : __ldg(reinterpret_cast<const cplx*>(colf_hp + mm[i].col_off));
+                        cf[i] = FSM ? lds_cplx(sa_colf + co) : __ldg(reinterpret_cast<const cplx*>(colf_hp + co));
                     }
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                    if (mm[i].row_off >= 0) out_base[mm[i].out_off] = cmul(cmul(v, rf[i]), cf[i]);
+                    if (mm[i].row_off >= 0) {
+                        const double sg = mm[i].col_off < 0 ? sflip : 1.0;
+                        out_base[mm[i].out_off] = cmul(cmul(cmake(v.x * sg, v.y * sg), rf[i]), cf[i]);
+                    }
             }
             for (int m = ASM_MEMCAP; m < cnt; ++m) {  // overflow of the shared-memory member list
                 const AsmMember mo = asm_member(__ldg(a.members + q0 + m), a.H, a.H * (int)sizeof(cplx), a.H * (int)sizeof(cplx),
                                                 a.b_lo, a.b_hi, hld);
-                if (mo.row_off >= 0)
-                    out_base[mo.out_off] = cmul(cmul(v, __ldg(reinterpret_cast<const cplx*>(rowf_h + mo.row_off))),
-                                                __ldg(reinterpret_cast<const cplx*>(colf_hp + mo.col_off)));
+                if (mo.row_off >= 0) {
+                    const double sg = mo.col_off < 0 ? sflip : 1.0;
+                    out_base[mo.out_off] = cmul(cmul(cmake(v.x * sg, v.y * sg), __ldg(reinterpret_cast<const cplx*>(rowf_h + mo.row_off))),
+                                                __ldg(reinterpret_cast<const cplx*>(colf_hp + (mo.col_off & 0x7fffffff))));
+                }
             }
         }
         q0 = q0n;
@@ -655,7 +687,7 @@ static bool asm_reg_shape(const bhs_plan* p, int B, int nsys, int* stage_bytes, 
     const int64_t sub = (int64_t)nsys * ucap * p->H2 * (int64_t)sizeof(cplx);
     if (stage_bytes) *stage_bytes = sb;
     if (su_bytes) *su_bytes = 0;
-    static const bool legacy = getenv("BHS_ASM_LEGACY") != nullptr;  // A/B switch: the shared-memory-resident kernel
+    const bool legacy = getenv("BHS_ASM_LEGACY") != nullptr;  // A/B switch (read per call): the shared-memory-resident kernel
     if (legacy || B < 2 || p->max_nt > 32 || (int64_t)p->max_sy_cnt * (int64_t)sizeof(cplx) > 48 * 1024 ||
         sub > ((int64_t)1 << 30))
         return false;
@@ -807,21 +839,24 @@ static int assemble_impl(const bhs_plan_t* plan, int B, int nsys, const double* 
         BHS_CHECK_LAUNCH();
     }
     // the search is O(np^2) in the worst case (no duplicates): bounded by skipping it for more than 128 spheres
+    int pm = 0;  // 1: pairs with opposite translations share a group (register-resident kernel; BHS_ASM_NOPM=1 turns it off)
     {
         const int dedupe = B <= 128 ? 1 : 0;
+        pm = (B > 1 && asm_reg_shape(plan, B, nsys, nullptr, nullptr) && getenv("BHS_ASM_NOPM") == nullptr) ? 1 : 0;
         size_t sm = (size_t)np * plan->d * sizeof(double);
         if (!dedupe || sm > 96 * 1024) sm = 0;
         if (sm > 48 * 1024) cudaFuncSetAttribute(pair_rep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        pair_rep_kernel<<<(unsigned)((np + 127) / 128), 128, sm, st>>>(plan->d, B, dedupe, w.tv, w.rep);
+        pair_rep_kernel<<<(unsigned)((np + 127) / 128), 128, sm, st>>>(plan->d, B, dedupe, pm, w.tv, w.rep);
     }
     BHS_CHECK_LAUNCH();
-    pair_group_kernel<<<1, 1024, 0, st>>>(B, w.rep, w.uid, w.cursor, w.n_unique, w.grp_rep, w.grp_start, w.members);
+    pair_group_kernel<<<1, 1024, 0, st>>>(B, plan->d, pm, w.tv, w.rep, w.uid, w.cursor, w.n_unique, w.grp_rep, w.grp_start,
+                                          w.members);
     BHS_CHECK_LAUNCH();
     AsmArgs a;
     a.B = B; a.H = plan->H; a.H2 = plan->H2; a.L2 = plan->L2;
     a.b_lo = b_lo; a.b_hi = b_hi;
     a.n_unique = w.n_unique; a.grp_rep = w.grp_rep; a.grp_start = w.grp_start; a.members = w.members;
-    a.tiles = plan->d_tiles; a.coef = plan->d_coef; a.cidx = plan->d_cidx; a.deg2 = plan->d_deg2;
+    a.tiles = plan->d_tiles; a.coef = plan->d_coef; a.cidx = plan->d_cidx; a.deg = plan->d_deg; a.deg2 = plan->d_deg2;
     a.Y2 = w.Y2; a.hp = w.hp; a.rowf = w.rowf; a.colf = w.colf; a.diag = w.diag;
     a.A = (cplx*)d_A; a.ld = ld; a.sys_stride = sys_stride;
     a.Su = w.Su; a.ucap = (int)(np - B);
@@ -840,30 +875,40 @@ static int assemble_impl(const bhs_plan_t* plan, int B, int nsys, const double* 
         }
         bhs_prof_end(BHS_PROF_ASM_PRE, 0.0, st);
         bhs_prof_begin(BHS_PROF_ASM_MAIN, st);
-        // about six waves of CTAs (two resident per SM): every CTA first loads its tile into registers (and stages its
-        // factors), so longer CTAs amortise that better, shorter ones balance the last wave better
-        int64_t chunks = (6 * 2 * bhs_sm_count() + (int64_t)ntiles * nsys - 1) / ((int64_t)ntiles * nsys);
-        if (chunks < 1) chunks = 1;
-        if (chunks > np - B) chunks = np - B;
-        if (chunks > 65535) chunks = 65535;
+        // Every CTA first loads its tile into registers (and stages its factors), so longer CTAs amortise that better,
+        // shorter ones balance the last wave better: between four and nine waves of CTAs (two resident per SM), the count
+        // whose last wave is fullest.
+        int64_t chunks = 1;
+        {
+            const double slots = 2.0 * bhs_sm_count(), per = (double)ntiles * nsys;
+            double best = -1.0;
+            const int64_t cmax = np - B;
+            for (int64_t c = 1; c <= cmax && c <= 65535; ++c) {
+                const double w = per * (double)c / slots;
+                if (w > 9.0 && best >= 0.0) break;
+                const double eff = w / ceil(w) - (w < 4.0 ? (4.0 - w) : 0.0);  // fewer than four waves only if nothing else fits
+                if (eff > best + 0.02) { best = eff; chunks = c; }
+            }
+        }
         dim3 grid((unsigned)ntiles, (unsigned)chunks, (unsigned)nsys);
         const bool fsm = B <= ASM_FSM_MAXB;
         const size_t smem = (size_t)2 * stage_bytes + (fsm ? (size_t)B * (BHS_TILE_R + BHS_TILE_C) * sizeof(cplx) : 0);
         const int nt_max = plan->max_nt;
+#define BHS_ASM_REG_LAUNCH2(NT, F)                                                                                     \
+    do {                                                                                                               \
+        cudaFuncSetAttribute(assemble_reg_kernel<NT, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+        assemble_reg_kernel<NT, F><<<grid, ASM_THREADS, smem, st>>>(a, stage_bytes);                                   \
+    } while (0)
 #define BHS_ASM_REG_LAUNCH(NT)                                                                                         \
     do {                                                                                                               \
-        if (fsm) {                                                                                                     \
-            cudaFuncSetAttribute(assemble_reg_kernel<NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
-            assemble_reg_kernel<NT, true><<<grid, ASM_THREADS, smem, st>>>(a, stage_bytes);                            \
-        } else {                                                                                                       \
-            cudaFuncSetAttribute(assemble_reg_kernel<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            assemble_reg_kernel<NT, false><<<grid, ASM_THREADS, smem, st>>>(a, stage_bytes);                           \
-        }                                                                                                              \
+        if (fsm) BHS_ASM_REG_LAUNCH2(NT, true);                                                                        \
+        else BHS_ASM_REG_LAUNCH2(NT, false);                                                                           \
     } while (0)
         if (nt_max <= 8) BHS_ASM_REG_LAUNCH(8);
         else if (nt_max <= 16) BHS_ASM_REG_LAUNCH(16);
         else if (nt_max <= 24) BHS_ASM_REG_LAUNCH(24);
         else BHS_ASM_REG_LAUNCH(32);
+#undef BHS_ASM_REG_LAUNCH2
 #undef BHS_ASM_REG_LAUNCH
         BHS_CHECK_LAUNCH();
         bhs_prof_end(BHS_PROF_ASM_MAIN, 16.0 * (double)(b_hi - b_lo) * plan->H * (double)N * nsys, st);
