@@ -12,13 +12,19 @@ struct StridedArr {
     __device__ __forceinline__ double& operator[](int n) const { return base[(size_t)n * stride]; }
 };
 
+// The order sequences sit in shared memory order-major with an ODD thread stride TS = T + 1: the recurrences (lane = argument,
+// consecutive addresses) and the transposed read of the store phase (lane = order, stride TS) are both bank-conflict free.
 __global__ void bessel_kernel(int d, int kind, int derivative, int n_max, int n_store, const double* __restrict__ x,
                               int64_t nx, cplx* __restrict__ out) {
     extern __shared__ __align__(16) double sm[];
-    const int T = blockDim.x;
-    StridedArr aj{sm + threadIdx.x, T};
-    StridedArr ay{sm + (size_t)n_store * T + threadIdx.x, T};
+    const int T = blockDim.x, TS = T + 1, L = n_max + 1;
+    StridedArr aj{sm + threadIdx.x, TS};
+    StridedArr ay{sm + (size_t)n_store * TS + threadIdx.x, TS};
     const bool want_j = kind != BHS_KIND_Y, want_y = kind != BHS_KIND_J;
+    const double* s_re = want_j ? sm : sm + (size_t)n_store * TS;
+    const double* s_im = sm + (size_t)n_store * TS;
+    // (argument, order) of the first element this thread stores, and the step to its next one (element e += T)
+    const int t_first = threadIdx.x / L, n_first = threadIdx.x % L, t_step = T / L, n_step = T % L;
     for (int64_t i0 = (int64_t)blockIdx.x * T; i0 < nx; i0 += (int64_t)gridDim.x * T) {
         int64_t i = i0 + threadIdx.x;
         double xv = (i < nx) ? x[i] : 1.0;
@@ -30,14 +36,17 @@ __global__ void bessel_kernel(int d, int kind, int derivative, int n_max, int n_
             }
         }
         __syncthreads();
-        int64_t cnt = nx - i0;
-        if (cnt > T) cnt = T;
-        int64_t total = cnt * (n_max + 1);
-        for (int64_t e = threadIdx.x; e < total; e += T) {
-            int t = (int)(e / (n_max + 1)), n = (int)(e % (n_max + 1));
-            double re = want_j ? sm[(size_t)n * T + t] : sm[((size_t)n_store + n) * T + t];
-            double im = (kind == BHS_KIND_H1) ? sm[((size_t)n_store + n) * T + t] : 0.0;
-            out[i0 * (n_max + 1) + e] = cmake(re, im);
+        const int cnt = (int)((nx - i0 < T) ? nx - i0 : T);
+        const int total = cnt * L;
+        cplx* o = out + i0 * L;
+        int t = t_first, n = n_first;
+        for (int e = threadIdx.x; e < total; e += T) {
+            const double re = s_re[n * TS + t];
+            const double im = (kind == BHS_KIND_H1) ? s_im[n * TS + t] : 0.0;
+            o[e] = cmake(re, im);
+            t += t_step;
+            n += n_step;
+            if (n >= L) { n -= L; ++t; }
         }
         __syncthreads();
     }
@@ -50,8 +59,8 @@ extern "C" int bhs_bessel(int d, int kind, int derivative, int n_max, const doub
     int shift = (d & 1) ? (d - 3) / 2 : d / 2 - 1;
     int n_store = n_max + 2 + shift + 1;
     int T = 128;
-    while (T > 32 && (size_t)2 * n_store * T * sizeof(double) > 160 * 1024) T >>= 1;
-    size_t smem = (size_t)2 * n_store * T * sizeof(double);
+    while (T > 32 && (size_t)2 * n_store * (T + 1) * sizeof(double) > 160 * 1024) T >>= 1;
+    size_t smem = (size_t)2 * n_store * (T + 1) * sizeof(double);
     if (smem > 200 * 1024) return BHS_ERR_UNSUPPORTED;
     cudaFuncSetAttribute(bessel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int64_t blocks = (nx + T - 1) / T;
