@@ -359,10 +359,10 @@ def point_source(*, k: Array, source: Array, n: int) -> tuple[Callable[[Array], 
 class _Slot:
     """Buffers of one group of `S` systems that are assembled and factorised in lock step."""
 
-    def __init__(self, d: int, n_end: int, B: int, N: int, S: int):
+    def __init__(self, d: int, n_end: int, B: int, N: int, S: int, priority: int = 0):
         dev = _dev()
         plan = get_plan(d, n_end)
-        self.stream = torch.cuda.Stream(device=dev)
+        self.stream = torch.cuda.Stream(device=dev, priority=priority)
         self.A = torch.empty((S, N, N), dtype=C128, device=dev)
         self.k = torch.ones((S,), dtype=F64, device=dev)
         self.k_im = torch.zeros((S,), dtype=F64, device=dev)
@@ -396,7 +396,10 @@ class SweepEngine:
         self.rad = torch.ones((B,), dtype=F64, device=dev)
         self.al = torch.ones((B,), dtype=C128, device=dev)
         self.be = torch.zeros((B,), dtype=C128, device=dev)
-        self.slots = [_Slot(d, n_end, B, self.N, batch) for _ in range(nslots)]
+        import os
+
+        nprio = max(1, int(os.environ.get("BHS_SWEEP_PRIO", "1")))
+        self.slots = [_Slot(d, n_end, B, self.N, batch, priority=-(i % nprio)) for i in range(nslots)]
         self.slot_bytes = nslots * batch * 16 * self.N * self.N
         # a CUDA graph buys nothing for one huge system (C5: N = 36 864, seconds per solve) and its warm-up pass would double it
         self.use_graphs = use_graphs and self.N <= 12000

@@ -585,16 +585,19 @@ __global__ void __launch_bounds__(ASM_THREADS, 2) assemble_reg_kernel(AsmArgs a,
     }
     // member lists live in shared memory padded to a multiple of four with inactive entries (row_off = -1); the rare
     // members beyond ASM_MEMCAP (more spheres than that sharing one translation) are written by the tail loop below
-    auto stage_members = [&](int buf, int q_first, int n) {
+    auto fetch_member = [&](int q_first, int n) -> int {  // the global load (issued early) ...
+        return (tid < n && tid < ASM_MEMCAP) ? __ldg(a.members + q_first + tid) : 0;
+    };
+    auto store_member = [&](int buf, int pk, int n) {  // ... and the decoded entry (stored once the buffer is free)
         const int n4 = min((n + 3) & ~3, ASM_MEMCAP);
         if (tid < n4) {
             AsmMember m;
             m.row_off = -1; m.col_off = 0; m.out_off = 0;
-            if (tid < n) m = asm_member(__ldg(a.members + q_first + tid), a.H, rs, cs, a.b_lo, a.b_hi, hld);
+            if (tid < n) m = asm_member(pk, a.H, rs, cs, a.b_lo, a.b_hi, hld);
             s_mem[buf][tid] = m;
         }
     };
-    stage_members(0, q0, cnt);
+    store_member(0, fetch_member(q0, cnt), cnt);
     __syncthreads();  // barrier inits, staged factors and s_mem[0] visible
 
     int it = 0;
@@ -631,8 +634,11 @@ __global__ void __launch_bounds__(ASM_THREADS, 2) assemble_reg_kernel(AsmArgs a,
                 }
             }
         }
-        stage_members(st ^ 1, q0n, cntn);
-        __syncthreads();  // everyone is done with stage st (refill it) and with s_mem[st ^ 1] of the previous translation
+        const int pk_next = fetch_member(q0n, cntn);
+        __syncthreads();  // everyone is done with stage st (refill it) and with the write phase of the previous translation,
+                          // i.e. with s_mem[st ^ 1]: only now may the next translation's members overwrite it (they are read
+                          // after the next barrier)
+        store_member(st ^ 1, pk_next, cntn);
         if (tid == 0) {
             const int u2 = u + 2 * ustep;
             if (u2 < U) {

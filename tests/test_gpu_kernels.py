@@ -178,6 +178,33 @@ def test_assemble_rows_strips(ops, d, n_end, B):
         assert torch.equal(strip, full[b_lo * H : b_hi * H])
 
 
+@pytest.mark.parametrize("d,half,n_end,nsys", [(3, 2, 16, 2), (3, 2, 16, 4), (3, 1, 7, 3), (2, 2, 20, 2), (3, 3, 10, 2), (3, 4, 6, 1)])
+def test_assemble_kernels_agree_bitwise(ops, monkeypatch, d, half, n_end, nsys):
+    """The register-resident assembly kernel against the shared-memory-resident one it replaced (BHS_ASM_LEGACY=1), on
+    regular grids (shared translations, many CTA iterations): bit-identical without the merging of opposite translations
+    (BHS_ASM_NOPM=1) and identical as numbers with it; repeated, because a race between warps of a CTA would show up as an
+    occasional difference (one did: the member list of the next translation overwrote the one still being read)."""
+    import torch
+
+    from biem_helmholtz_sphere_b200.geometry import grid_centers
+
+    cen = torch.as_tensor(grid_centers(half, d), device="cuda")
+    B = cen.shape[0]
+    g = torch.Generator(device="cuda").manual_seed(3)
+    rad = 0.5 + 0.4 * torch.rand(B, dtype=torch.float64, device="cuda", generator=g)
+    k = torch.linspace(0.7, 2.9, nsys, dtype=torch.float64, device="cuda")
+    monkeypatch.setenv("BHS_ASM_LEGACY", "1")
+    want = ops.assemble(d, n_end, cen, rad, k, k)
+    monkeypatch.delenv("BHS_ASM_LEGACY")
+    for rep in range(4):
+        monkeypatch.setenv("BHS_ASM_NOPM", "1")
+        got = ops.assemble(d, n_end, cen, rad, k, k)
+        assert torch.equal(got.view(torch.float64).view(torch.int64), want.view(torch.float64).view(torch.int64)), rep
+        monkeypatch.delenv("BHS_ASM_NOPM")
+        got = ops.assemble(d, n_end, cen, rad, k, k)
+        assert torch.equal(got, want), rep  # equal as numbers (signed zeros may differ)
+
+
 @pytest.mark.parametrize("M,N,K", [(64, 64, 8), (128, 192, 32), (200, 77, 40), (1000, 520, 128), (37, 5, 16)])
 def test_zgemm_sub(ops, M, N, K):
     import torch
