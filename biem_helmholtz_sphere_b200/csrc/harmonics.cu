@@ -36,10 +36,148 @@ __global__ void __launch_bounds__(128) harmonics_kernel(HarmTables tb, int Lb, c
     }
 }
 
+// ---- 3-D specialisation ------------------------------------------------------------------------------------------
+// Same tables, same recurrences and the same products as the generic kernel (so the values are identical), organised for
+// throughput: a HALF-warp builds the tables of one direction (lane l runs the degree recurrence of the node functions f_{n,l},
+// n >= l, and the power e^{i l phi}), i.e. a warp prepares two directions at once with every lane busy; the whole warp then
+// streams each direction's H values out, 512 contiguous bytes per store instruction.  The (n, |m|, sign) of the harmonics a
+// lane stores are direction-independent: they are unpacked once into NH registers per lane (NH = 0: read per use).
+// The generic kernel spent ~1350 instructions per direction (run-time tree depth, 64-bit index arithmetic, local-memory
+// coordinate arrays); this one ~300.
+template <int NH>
+__global__ void __launch_bounds__(128) harmonics3d_kernel(HarmTables tb, int Lb, const int32_t* __restrict__ idx, int Hb,
+                                                          const double* __restrict__ xyz, int64_t npts,
+                                                          const double* __restrict__ scale, int conj_out,
+                                                          cplx* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int half = lane >> 4, hl = lane & 15;
+    const size_t per_dir = harm_smem_bytes_per_warp(3, Lb);
+    unsigned char* wbase = smem_raw + per_dir * 2 * warp;
+    double* F;
+    cplx* E;
+    harm_smem_carve(wbase + per_dir * half, Lb, F, E);
+    // packed (F offset | |m| << 12 | negative-m << 20) of this lane's harmonics
+    int pk[NH > 0 ? NH : 1];
+    auto pack = [&](int h) {
+        const int2 nm = *reinterpret_cast<const int2*>(idx + (int64_t)h * 2);
+        const int am = nm.y < 0 ? -nm.y : nm.y;
+        return (nm.x * Lb + am) | (am << 12) | ((nm.y < 0) << 20);
+    };
+    if (NH > 0) {
+#pragma unroll
+        for (int j = 0; j < NH; ++j) pk[j] = (lane + 32 * j < Hb) ? pack(lane + 32 * j) : 0;
+    }
+    const double inv_s2pi = 0.39894228040143267794;
+    for (int64_t p0 = 2 * ((int64_t)blockIdx.x * warps + warp); p0 < npts; p0 += 2 * (int64_t)gridDim.x * warps) {
+        const int64_t p = p0 + half;
+        if (p < npts) {
+            const double x0 = xyz[p], x1 = xyz[npts + p], x2 = xyz[2 * npts + p];
+            // tails as in warp_harmonic_tables: accumulated from the last coordinate
+            double acc = x2 * x2;
+            acc += x1 * x1;
+            const double t1 = sqrt(acc);
+            acc += x0 * x0;
+            const double t0 = sqrt(acc);
+            double ct = 1.0, st = 0.0;
+            if (t0 > 0.0) {
+                ct = x0 / t0;
+                st = t1 / t0;
+            }
+            double cp = 1.0, sp = 0.0;
+            if (t1 > 0.0) {
+                cp = x1 / t1;
+                sp = x2 / t1;
+            }
+            for (int l = hl; l < Lb; l += 16) {
+                const double f0 = tb.all[l] * powi_d(st, l);
+                F[l * Lb + l] = f0;
+                double fm2 = 0.0, fm1 = f0;
+                const double* c1 = tb.c1 + l;
+                const double* c2 = tb.c2 + l;
+                for (int n = l + 1; n < Lb; ++n) {
+                    const double f = c1[(size_t)n * tb.L2] * ct * fm1 - c2[(size_t)n * tb.L2] * fm2;
+                    F[n * Lb + l] = f;
+                    fm2 = fm1;
+                    fm1 = f;
+                }
+                cplx r = cmake(1.0, 0.0), b = cmake(cp, sp);
+                int e = l;
+                while (e) {
+                    if (e & 1) r = cmul(r, b);
+                    b = cmul(b, b);
+                    e >>= 1;
+                }
+                E[l] = cscale(r, inv_s2pi);
+            }
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int q = 0; q < 2; ++q) {
+            const int64_t pq = p0 + q;
+            if (pq >= npts) break;
+            const double* Fq;
+            const cplx* Eq;
+            {
+                double* f_;
+                cplx* e_;
+                harm_smem_carve(wbase + per_dir * q, Lb, f_, e_);
+                Fq = f_;
+                Eq = e_;
+            }
+            const double sc = scale ? scale[pq] : 1.0;
+            cplx* o = out + pq * Hb;
+            if (NH > 0) {
+#pragma unroll
+                for (int j = 0; j < NH; ++j) {
+                    const int h = lane + 32 * j;
+                    if (h < Hb) {
+                        const int w = pk[j];
+                        cplx e = Eq[(w >> 12) & 0xff];
+                        if ((w >> 20) != conj_out) e.y = -e.y;  // conj for negative m, once more for a conjugated output
+                        const double prod = 1.0 * Fq[w & 0xfff];
+                        o[h] = cscale(cscale(e, prod), sc);
+                    }
+                }
+            } else {
+                for (int h = lane; h < Hb; h += 32) {
+                    const int w = pack(h);
+                    cplx e = Eq[(w >> 12) & 0xff];
+                    if ((w >> 20) != conj_out) e.y = -e.y;
+                    const double prod = 1.0 * Fq[w & 0xfff];
+                    o[h] = cscale(cscale(e, prod), sc);
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 static int launch_harmonics(const bhs_plan* plan, int Lb, const int32_t* d_idx, int Hb, const double* d_xyz,
                             int64_t npts, const double* d_scale, int conj_out, cplx* d_out, cudaStream_t st) {
     if (npts <= 0) return BHS_OK;
     HarmTables tb = harm_tables_of(plan);
+    if (plan->d == 3 && Lb <= 64 && getenv("BHS_HARM_GENERIC") == nullptr) {  // F offsets are packed in 12 bits, |m| in 8
+        const int warps = 4;
+        const size_t smem = harm_smem_bytes_per_warp(3, Lb) * 2 * warps;
+        int64_t blocks = (npts + 2 * warps - 1) / (2 * warps);
+        const int per_sm = (int)((200 * 1024) / (smem + 1024)) < 8 ? (int)((200 * 1024) / (smem + 1024)) : 8;
+        if (blocks > (int64_t)bhs_sm_count() * per_sm) blocks = (int64_t)bhs_sm_count() * per_sm;
+        if (smem <= 200 * 1024 && per_sm >= 1) {
+#define BHS_H3_LAUNCH(NH)                                                                                       \
+    do {                                                                                                        \
+        cudaFuncSetAttribute(harmonics3d_kernel<NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+        harmonics3d_kernel<NH><<<(unsigned)blocks, warps * 32, smem, st>>>(tb, Lb, d_idx, Hb, d_xyz, npts, d_scale, \
+                                                                          conj_out, d_out);                     \
+    } while (0)
+            if (Hb <= 256) BHS_H3_LAUNCH(8);
+            else if (Hb <= 1024) BHS_H3_LAUNCH(32);
+            else BHS_H3_LAUNCH(0);
+#undef BHS_H3_LAUNCH
+            BHS_CHECK_LAUNCH();
+            return BHS_OK;
+        }
+    }
     int warps = 4;
     while (warps > 1 && harm_smem_bytes_per_warp(plan->d, Lb) * warps > 200 * 1024) warps >>= 1;
     size_t smem = harm_smem_bytes_per_warp(plan->d, Lb) * warps;
