@@ -57,6 +57,15 @@ __global__ void __launch_bounds__(128) harmonics3d_kernel(HarmTables tb, int Lb,
     double* F;
     cplx* E;
     harm_smem_carve(wbase + per_dir * half, Lb, F, E);
+    // the recurrence coefficients of the band, staged once per CTA ([n][l], l fastest: conflict-free for lane = l)
+    double* s_c1 = reinterpret_cast<double*>(smem_raw + per_dir * 2 * warps);
+    double* s_c2 = s_c1 + Lb * Lb;
+    for (int e = threadIdx.x; e < Lb * Lb; e += blockDim.x) {
+        const int n = e / Lb, l = e - n * Lb;
+        s_c1[e] = tb.c1[(size_t)n * tb.L2 + l];
+        s_c2[e] = tb.c2[(size_t)n * tb.L2 + l];
+    }
+    __syncthreads();
     // packed (F offset | |m| << 12 | negative-m << 20) of this lane's harmonics
     int pk[NH > 0 ? NH : 1];
     auto pack = [&](int h) {
@@ -93,10 +102,8 @@ __global__ void __launch_bounds__(128) harmonics3d_kernel(HarmTables tb, int Lb,
                 const double f0 = tb.all[l] * powi_d(st, l);
                 F[l * Lb + l] = f0;
                 double fm2 = 0.0, fm1 = f0;
-                const double* c1 = tb.c1 + l;
-                const double* c2 = tb.c2 + l;
                 for (int n = l + 1; n < Lb; ++n) {
-                    const double f = c1[(size_t)n * tb.L2] * ct * fm1 - c2[(size_t)n * tb.L2] * fm2;
+                    const double f = s_c1[n * Lb + l] * ct * fm1 - s_c2[n * Lb + l] * fm2;
                     F[n * Lb + l] = f;
                     fm2 = fm1;
                     fm1 = f;
@@ -158,8 +165,10 @@ static int launch_harmonics(const bhs_plan* plan, int Lb, const int32_t* d_idx, 
     if (npts <= 0) return BHS_OK;
     HarmTables tb = harm_tables_of(plan);
     if (plan->d == 3 && Lb <= 64 && getenv("BHS_HARM_GENERIC") == nullptr) {  // F offsets are packed in 12 bits, |m| in 8
-        const int warps = 4;
-        const size_t smem = harm_smem_bytes_per_warp(3, Lb) * 2 * warps;
+        int warps = 4;
+        const size_t coef_bytes = (size_t)2 * Lb * Lb * sizeof(double);
+        while (warps > 1 && harm_smem_bytes_per_warp(3, Lb) * 2 * warps + coef_bytes > 200 * 1024) warps >>= 1;
+        const size_t smem = harm_smem_bytes_per_warp(3, Lb) * 2 * warps + coef_bytes;
         int64_t blocks = (npts + 2 * warps - 1) / (2 * warps);
         const int per_sm = (int)((200 * 1024) / (smem + 1024)) < 8 ? (int)((200 * 1024) / (smem + 1024)) : 8;
         if (blocks > (int64_t)bhs_sm_count() * per_sm) blocks = (int64_t)bhs_sm_count() * per_sm;
