@@ -1454,6 +1454,7 @@ struct LuCtx {
     double* Up;
     int nks_total;      // LU_NBO / G_KC
     int64_t J;          // current outer block start (anchor of Lp rows and of the stage index)
+    int nbo;            // outer block width of this factorisation: LU_NBO, or a multiple of it (see lu_factor)
     int nbatch;         // systems factorised in lock step (grid z)
     LuBatch bs;
     cudaStream_t st;
@@ -1679,19 +1680,19 @@ static void lu_trsm(LuCtx& x, int64_t j0, int T, int64_t c_lo, int64_t c_hi) {
         lu_pack_u(x, j0, T, c_lo, c_hi);
         return;
     }
-    int h = (T > 64) ? 64 : 32;
+    int h = (T > 128) ? 128 : (T > 64) ? 64 : 32;
     lu_trsm(x, j0, h, c_lo, c_hi);
     lu_gemm(x, j0 + h, j0 + T, c_lo, c_hi, j0, h);
     lu_trsm(x, j0 + h, T - h, c_lo, c_hi);
 }
 
-// recursive LU of columns [j0, j0+w) (rows j0..N), w <= 128
+// recursive LU of columns [j0, j0+w) (rows j0..N), w <= the outer block width
 static void lu_rec(LuCtx& x, int64_t j0, int w) {
     if (w <= LU_NB) {
         lu_panel(x, j0, w);
         return;
     }
-    int h = (w > 64) ? 64 : 32;
+    int h = (w > 128) ? 128 : (w > 64) ? 64 : 32;
     lu_rec(x, j0, h);
     lu_trsm(x, j0, h, j0 + h, j0 + w);
     lu_gemm(x, j0 + h, x.N, j0 + h, j0 + w, j0, h);
@@ -1804,11 +1805,18 @@ static int lu_factor(LuCtx& x) {
         cudaStream_t pst = lu_panel_stream();
         if (pst) {
             x.lookahead = true;
+            x.nbo = LU_NBO;
             return lu_factor_lookahead(x, pst);
         }
     }
-    for (int64_t J = 0; J < x.N; J += LU_NBO) {
-        int w = (int)((x.N - J < LU_NBO) ? (x.N - J) : LU_NBO);
+    // Outer block width without look-ahead: 256 with the tensor-map GEMM.  The trailing update then runs 256-deep k loops (half
+    // as many passes over C, a longer steady state per tile), at the price of a 128-deep update inside the block; the panel chain
+    // gets longer, which only matters for a lone system (those take the look-ahead path above, 128 wide).  BHS_LU_NBO overrides.
+    static const int nbo_env = [] { const char* e = getenv("BHS_LU_NBO"); return e ? atoi(e) : 0; }();
+    x.nbo = x.tma ? 256 : LU_NBO;
+    if (nbo_env >= LU_NBO && nbo_env % LU_NBO == 0 && x.tma) x.nbo = nbo_env;
+    for (int64_t J = 0; J < x.N; J += x.nbo) {
+        int w = (int)((x.N - J < x.nbo) ? (x.N - J) : x.nbo);
         x.J = J;
         if (gemm_only) {
             if (J + w < x.N) {
@@ -1818,7 +1826,8 @@ static int lu_factor(LuCtx& x) {
             continue;
         }
         lu_rec(x, J, w);
-        if (x.rhs) lu_rhs_forward(x, J, w);
+        if (x.rhs)  // (the block solve works on 128-wide blocks)
+            for (int o = 0; o < w; o += LU_NBO) lu_rhs_forward(x, J + o, (w - o < LU_NBO) ? w - o : LU_NBO);
         if (J + w < x.N) {
             lu_trsm(x, J, w, J + w, x.N);
             lu_gemm(x, J + w, x.N, J + w, x.N, J, w);
