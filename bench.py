@@ -14,8 +14,9 @@ i mod N (no data-path collective; total work fixed => "scaling": "strong").
 `e2e`    : systems/s through the reference-shaped public API with HOST (NumPy) inputs and outputs: the H2D copies
            of the inputs and the D2H copies of density + u_scat are inside the timed region.  `e2e.c5` is the second
            half of the metric measured the same way (see below).
-`roofline`: the LU trailing update (zgemm_tma_kernel, FP64 DMMA) -- flops of its launches / their summed CUDA-event
-           durations inside one profiled sweep pass, against the FP64 tensor peak measured in the same run
+`roofline`: the LU trailing update (zgemm3m_tma_kernel, FP64 DMMA) -- flops of its launches / their summed CUDA-event
+           durations inside one eager pass of a sweep group (the launches the sweep's graphs replay: `batch` systems per
+           bhs_zgesv_batched call), against the FP64 tensor peak measured in the same run
            (MEASURED_PEAKS.json has no FP64 entry; the cuBLAS ZGEMM 8192^3 cross-check is printed beside it).
            `roofline.uscat`, `roofline.c5_lu` and `roofline.assembly` carry the other kernels of the metric.
 `c5`     : config C5 end to end through the public API (default on): biem(keep_matrix=False) of the 64-sphere, n_end = 24
@@ -381,7 +382,7 @@ def run_b200(args) -> None:
 
     # ---- per-kernel split + roofline of the LU trailing update (rank 0, eager profiled pass) -------------
     if rank == 0:
-        traffic = _load_profile("r02_zgemm_traffic.json") or _load_profile("r01_zgemm_traffic.json")
+        traffic = _load_profile("r02c_zgemm_traffic.json") or _load_profile("r02_zgemm_traffic.json")
         peaks = {"dfma": _ops.fp64_peak(0, 4096), "dmma884": _ops.fp64_peak(1, 4096), "dmma1684": _ops.fp64_peak(2, 2048),
                  "dmma1688": _ops.fp64_peak(3, 1024), "dmma16816": _ops.fp64_peak(4, 512)}
         # cross-check of the tensor peak with the vendor library: cuBLAS ZGEMM 8192^3 (8 real flops per complex FMA)
@@ -399,24 +400,48 @@ def run_b200(args) -> None:
                          "DMMA.8x8x4 on sm_100a, profiles/r02_fp64_mma_shapes.txt); cublas_zgemm_8192: torch.matmul complex128")
         peak_dmma = max(peaks["dmma884"], 1e-9)
         peak_dfma = max(peaks["dfma"], 1e-9)
-        nprof = min(4, K)
-        A = torch.empty((1, N, N), dtype=C128, device=dev)
-        work = _ops._work(_ops.load().bhs_assemble_workspace(_ops.get_plan(3, N_END).handle, B, 1))
+        # Profiled pass = what the sweep's graphs replay: ONE group of `sweep_batch` systems through bhs_assemble (nsys = batch)
+        # and bhs_zgesv_batched, launched eagerly with an event pair around every launch (bhs_profile).  A second pass times a
+        # lone system through bhs_zgesv (cluster panels + look-ahead), for kernel_split_lone_ms.
+        nprof = max(1, min(sweep_batch, K))
+        A = torch.empty((nprof, N, N), dtype=C128, device=dev)
+        work = _ops._work(_ops.load().bhs_assemble_workspace(_ops.get_plan(3, N_END).handle, B, nprof))
+        bufs_b = _ops.SolveBuffers(N, 1, nprof)
         bufs = _ops.SolveBuffers(N, 1)
+
+        def group_pass():
+            f = _ops.rhs_expand(3, N_END, centers=cen_d, radii=rad_d, k_in=ks_d[:nprof], direction=dir_d.reshape(3))
+            _ops.assemble(3, N_END, cen_d, rad_d, ks_d[:nprof], eta_d[:nprof], out=A, work=work)
+            r = f.reshape(nprof, N).clone()
+            _ops.zgesv_batched_(A, r, bufs_b)
+            for i in range(nprof):
+                _ops.uscat(3, N_END, cen_d, rad_d, float(ks_np[i]), 1.0, r[i].reshape(B, H), x_d)
+            return f
+
+        def lone_pass():
+            f = _ops.rhs_expand(3, N_END, centers=cen_d, radii=rad_d, k_in=ks_d[:1], direction=dir_d.reshape(3))
+            _ops.assemble(3, N_END, cen_d, rad_d, ks_d[:1], eta_d[:1], out=A[:1], work=work)
+            r = f.reshape(N).clone()
+            _ops.zgesv_(A[0], r, bufs)
+            _ops.uscat(3, N_END, cen_d, rad_d, float(ks_np[0]), 1.0, r.reshape(B, H), x_d)
+            return f
+
+        group_pass()  # untimed: loads every kernel of the batched path
         torch.cuda.synchronize()
+        _ops.profile(True)
+        lone_pass()
+        torch.cuda.synchronize()
+        prof_lone = _ops.profile_read()
+        _ops.profile(False)
         _ops.profile(True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(nprof):
-            f = _ops.rhs_expand(3, N_END, centers=cen_d, radii=rad_d, k_in=ks_d[i:i + 1], direction=dir_d.reshape(3))
-            _ops.assemble(3, N_END, cen_d, rad_d, ks_d[i:i + 1], eta_d[i:i + 1], out=A, work=work)
-            r = f.reshape(N).clone()
-            _ops.zgesv_(A[0], r, bufs)
-            _ops.uscat(3, N_END, cen_d, rad_d, float(ks_np[i]), 1.0, r.reshape(B, H), x_d)
+        f = group_pass()
         e1.record()
         torch.cuda.synchronize()
         prof = _ops.profile_read()
         _ops.profile(False)
+        f = f[:1]
         tot_ms = e0.elapsed_time(e1)
         g = prof["lu_gemm"]
         gemm_tf = g["work"] / (g["ms"] * 1e-3) * 1e-12 if g["ms"] > 0 else 0.0
@@ -439,8 +464,9 @@ def run_b200(args) -> None:
             + str(traffic.get("algorithmic_bytes")) + ")",
             "launches": int(g["count"]), "avg_launch_ms": g["ms"] / max(g["count"], 1),
             "flops_per_launch_avg": g["work"] / max(g["count"], 1),
-            "scope": "trailing updates of the 128-wide outer blocks (97.7 % of the LU flops), every launch of the "
-                     "profiled pass; the K = 32/64 updates inside the panel recursion are reported under inner_updates",
+            "scope": f"every update with K >= 128 of one group of {nprof} systems factorised in lock step by bhs_zgesv_batched -- the "
+                     "launches the sweep's CUDA graphs replay (256-wide outer blocks: K = 256 trailing updates, K = 128 updates "
+                     "inside a block); the K = 32/64 updates inside the panel recursion are reported under inner_updates",
             "inner_updates": {"tflops": gi["work"] / (gi["ms"] * 1e-3) * 1e-12 if gi["ms"] > 0 else None,
                               "launches": int(gi["count"]), "ms_per_system": gi["ms"] / nprof},
             "fp64_peaks": peaks,
@@ -473,10 +499,13 @@ def run_b200(args) -> None:
         del La, Ua, Ca, wk
         out["kernel_split_ms_per_system"] = {n: v["ms"] / nprof for n, v in prof.items()}
         out["kernel_split_ms_per_system"]["eager_total"] = tot_ms / nprof
-        out["kernel_split_note"] = "ONE lone system, eager launches (bhs_zgesv: cluster-resident panels); the sweep runs bhs_zgesv_batched"
+        out["kernel_split_note"] = (f"one group of {nprof} systems in lock step (bhs_assemble nsys = {nprof}, bhs_zgesv_batched), eager "
+                                    "launches, per system; kernel_split_lone_ms: ONE lone system through bhs_zgesv (cluster panels, look-ahead)")
+        out["kernel_split_lone_ms"] = {n: v["ms"] for n, v in prof_lone.items()}
+        lu_ms = sum(prof_lone[n]["ms"] for n in ("lu_gemm", "lu_gemm_inner", "lu_panel", "lu_trsm", "lu_pack", "lu_rhs"))
         # a lone system as a CUDA graph (what the sweep engine replays), timed alone
         Ag = torch.empty((N, N), dtype=C128, device=dev)
-        _ops.assemble(3, N_END, cen_d, rad_d, ks_d[:1], eta_d[:1], out=A, work=work)
+        _ops.assemble(3, N_END, cen_d, rad_d, ks_d[:1], eta_d[:1], out=A[:1], work=work)
         rg = f.reshape(N).clone()
         side = torch.cuda.Stream()
         with torch.cuda.stream(side):
@@ -498,7 +527,7 @@ def run_b200(args) -> None:
         lu_graph_ms = tg / 5
         flops_lu = (8.0 / 3.0) * N ** 3
         out["lu"] = {"tflops": flops_lu / (lu_graph_ms * 1e-3) * 1e-12, "ms": lu_graph_ms,
-                     "eager_ms": lu_ms / nprof, "eager_tflops": flops_lu / (lu_ms / nprof * 1e-3) * 1e-12 if lu_ms > 0 else None,
+                     "eager_ms": lu_ms, "eager_tflops": flops_lu / (lu_ms * 1e-3) * 1e-12 if lu_ms > 0 else None,
                      "frac_of_dmma_peak": flops_lu / (lu_graph_ms * 1e-3) * 1e-12 / peak_dmma,
                      "what": "ONE N = 4096 system factorised and solved alone (bhs_zgesv as a CUDA graph; eager_*: plain launches)",
                      "fp64_dmma_peak_tflops": peak_dmma, "fp64_dfma_peak_tflops": peak_dfma}
@@ -526,7 +555,7 @@ def run_b200(args) -> None:
                                        "figure (read + write bytes); write_stream_gbs is a 4 GiB fill measured in this run"}
             out["roofline"]["assembly"] = {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm}
         out["special_functions"] = _bench_special(torch, _ops, dev, hbm)
-        del A, work, bufs
+        del A, work, bufs, bufs_b
 
     # ---- C5: the 36 864-unknown system + the 2048^2 field map through the public API, field rows split over the ranks ----
     if not args.no_c5:
