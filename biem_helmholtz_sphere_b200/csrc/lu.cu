@@ -1455,6 +1455,7 @@ struct LuCtx {
     int nks_total;      // LU_NBO / G_KC
     int64_t J;          // current outer block start (anchor of Lp rows and of the stage index)
     int nbo;            // outer block width of this factorisation: LU_NBO, or a multiple of it (see lu_factor)
+    bool defer_perm;    // panels interchange rows inside their outer block only; the other columns follow once per block
     int nbatch;         // systems factorised in lock step (grid z)
     LuBatch bs;
     cudaStream_t st;
@@ -1506,10 +1507,20 @@ static LuWork lu_carve(int64_t N, int nbatch, void* base) {
         if (e__ != cudaSuccess && !(ctx).err) (ctx).err = (int)e__; \
     } while (0)
 
+// BHS_LU_SKIP (measurement aid, WRONG results): bit mask of kernel families that are not launched, to see what each costs a
+// sweep -- 1: pivot selection + interchanges + L21 (the whole panel), 2: interchanges only, 4: 32-row triangular solves,
+// 8: updates with K < 128, 16: right-hand-side kernels, 32: the K = 128 update inside a 256-wide block, 64: the K = 128 update
+// inside its U12 solve.
+static int lu_skip_mask() {
+    static const int m = [] { const char* e = getenv("BHS_LU_SKIP"); return e ? atoi(e) : 0; }();
+    return m;
+}
+
 // C[rows r_lo.., cols c_lo..c_hi) -= L[rows, k0..k0+K) * U[k0..k0+K, cols]   (operands already packed)
 static void lu_pack_l(LuCtx& x, int64_t r_lo, int64_t r_hi, int64_t k0, int K);
 static void lu_gemm(LuCtx& x, int64_t r_lo, int64_t r_hi, int64_t c_lo, int64_t c_hi, int64_t k0, int K) {
     if (r_lo >= r_hi || c_lo >= c_hi || K <= 0) return;
+    if ((lu_skip_mask() & 8) && K < LU_NBO) return;
     const int pcat = (K >= LU_NBO || (k0 == x.J && r_lo >= x.J + LU_NBO)) ? BHS_PROF_LU_GEMM : BHS_PROF_LU_GEMM_IN;
     if (x.tma) {
         bhs_prof_begin(pcat, x.st);
@@ -1590,6 +1601,7 @@ static void cluster_init() {
 
 // 32-wide (or narrower) panel at column j: pivot selection, swap, diagonal LU, L21
 static void lu_panel(LuCtx& x, int64_t j, int w) {
+    if (lu_skip_mask() & 1) return;
     const int64_t M = x.N - j;
     int64_t nsets = cdiv64(M, LU_R);
     int cur = 0;
@@ -1651,11 +1663,12 @@ static void lu_panel(LuCtx& x, int64_t j, int w) {
             nsets = nsets2;
         }
     }
-    {
+    if (!(lu_skip_mask() & 2)) {
         // row interchanges: every column (and the right-hand sides) now -- or, with look-ahead, only the columns of the outer
         // block being factorised; the columns left and right of it follow on the side stream (lu_permute_deferred)
-        const int64_t c_lo = x.lookahead ? x.J : 0;
-        const int64_t c_hi = x.lookahead ? (x.J + LU_NBO < x.N ? x.J + LU_NBO : x.N) : x.N;
+        const bool local = x.lookahead || x.defer_perm;
+        const int64_t c_lo = local ? x.J : 0;
+        const int64_t c_hi = local ? (x.J + x.nbo < x.N ? x.J + x.nbo : x.N) : x.N;
         const int nct = (int)cdiv64(c_hi - c_lo, PERM_COLS), nrt = x.rhs ? (int)cdiv64(x.nrhs, PERM_COLS) : 0;
         lu_permute_kernel<<<dim3((unsigned)(nct + nrt), 1, x.nbatch), 256, 0, x.st>>>(
             x.A, x.ld, c_lo, c_hi - c_lo, nct, x.rhs, x.nrhs, j, 1, w, x.dblk, pmap_j, x.bs.sA, x.bs.sRhs, x.bs.sDblk, x.bs.sPmap);
@@ -1672,6 +1685,7 @@ static void lu_panel(LuCtx& x, int64_t j, int w) {
 static void lu_trsm(LuCtx& x, int64_t j0, int T, int64_t c_lo, int64_t c_hi) {
     if (c_lo >= c_hi || T <= 0) return;
     if (T <= LU_NB) {
+        if (lu_skip_mask() & 4) return;
         bhs_prof_begin(BHS_PROF_LU_TRSM, x.st);
         lu_trsm32_kernel<<<dim3((unsigned)cdiv64(c_hi - c_lo, 128), 1, x.nbatch), 128, 0, x.st>>>(x.A, x.ld, j0, T, x.A, x.ld, c_lo,
                                                                                                   c_hi, x.bs.sA);
@@ -1682,7 +1696,7 @@ static void lu_trsm(LuCtx& x, int64_t j0, int T, int64_t c_lo, int64_t c_hi) {
     }
     int h = (T > 128) ? 128 : (T > 64) ? 64 : 32;
     lu_trsm(x, j0, h, c_lo, c_hi);
-    lu_gemm(x, j0 + h, j0 + T, c_lo, c_hi, j0, h);
+    if (!((lu_skip_mask() & 64) && h >= LU_NBO)) lu_gemm(x, j0 + h, j0 + T, c_lo, c_hi, j0, h);
     lu_trsm(x, j0 + h, T - h, c_lo, c_hi);
 }
 
@@ -1695,14 +1709,14 @@ static void lu_rec(LuCtx& x, int64_t j0, int w) {
     int h = (w > 128) ? 128 : (w > 64) ? 64 : 32;
     lu_rec(x, j0, h);
     lu_trsm(x, j0, h, j0 + h, j0 + w);
-    lu_gemm(x, j0 + h, x.N, j0 + h, j0 + w, j0, h);
+    if (!((lu_skip_mask() & 32) && h >= LU_NBO)) lu_gemm(x, j0 + h, x.N, j0 + h, j0 + w, j0, h);
     lu_rec(x, j0 + h, w - h);
 }
 
 // The interchanges of the panels of the outer block at J, applied to the columns [c_lo, c_hi) that the panel-time launches
 // skipped (look-ahead).
 static void lu_permute_deferred(LuCtx& x, int64_t J, int w, int64_t c_lo, int64_t c_hi) {
-    if (c_lo >= c_hi) return;
+    if (c_lo >= c_hi || (lu_skip_mask() & 3)) return;
     const int npan = (w + LU_NB - 1) / LU_NB, wlast = w - (npan - 1) * LU_NB;
     const int nct = (int)cdiv64(c_hi - c_lo, PERM_COLS);
     bhs_prof_begin(BHS_PROF_LU_PANEL, x.st);
@@ -1714,6 +1728,7 @@ static void lu_permute_deferred(LuCtx& x, int64_t J, int w, int64_t c_lo, int64_
 }
 
 static void lu_rhs_forward(LuCtx& x, int64_t J, int w) {
+    if (lu_skip_mask() & 16) return;
     // forward substitution of this block row: y_J = L11^{-1} rhs_J ; rhs_below -= L21 y_J
     bhs_prof_begin(BHS_PROF_LU_RHS, x.st);
     rhs_block_solve_kernel<<<dim3(1, 1, x.nbatch), 128, RS_SMEM, x.st>>>(x.A, x.ld, J, w, 0, x.rhs, x.nrhs, x.bs.sA, x.bs.sRhs);
@@ -1801,6 +1816,7 @@ static int lu_factor(LuCtx& x) {
     // at N = 36 864: 4.46 s without, 4.81 s with look-ahead; at N = 8192: 86 ms without, 69 ms with.
     static const int la_mode = [] { const char* e = getenv("BHS_LU_LOOKAHEAD"); return e ? atoi(e) : 1; }();
     x.lookahead = false;
+    x.defer_perm = false;
     if (!gemm_only && x.tma && la_mode && (la_mode >= 2 || (x.nbatch == 1 && x.N <= 12288)) && x.N > 2 * LU_NBO) {
         cudaStream_t pst = lu_panel_stream();
         if (pst) {
@@ -1814,6 +1830,8 @@ static int lu_factor(LuCtx& x) {
     // gets longer, which only matters for a lone system (those take the look-ahead path above, 128 wide).  BHS_LU_NBO overrides.
     static const int nbo_env = [] { const char* e = getenv("BHS_LU_NBO"); return e ? atoi(e) : 0; }();
     x.nbo = x.tma ? 256 : LU_NBO;
+    static const bool defer_off = getenv("BHS_LU_PERM_NOW") != nullptr;  // A/B: every panel interchanges all N columns at once
+    x.defer_perm = !gemm_only && !defer_off;
     if (nbo_env >= LU_NBO && nbo_env % LU_NBO == 0 && x.tma) x.nbo = nbo_env;
     for (int64_t J = 0; J < x.N; J += x.nbo) {
         int w = (int)((x.N - J < x.nbo) ? (x.N - J) : x.nbo);
@@ -1826,6 +1844,10 @@ static int lu_factor(LuCtx& x) {
             continue;
         }
         lu_rec(x, J, w);
+        if (x.defer_perm) {  // the interchanges of the block's panels on the columns left and right of it, all panels per launch
+            lu_permute_deferred(x, J, w, 0, J);
+            lu_permute_deferred(x, J, w, J + w, x.N);
+        }
         if (x.rhs)  // (the block solve works on 128-wide blocks)
             for (int o = 0; o < w; o += LU_NBO) lu_rhs_forward(x, J + o, (w - o < LU_NBO) ? w - o : LU_NBO);
         if (J + w < x.N) {
@@ -1837,6 +1859,7 @@ static int lu_factor(LuCtx& x) {
 }
 
 static int lu_backward(LuCtx& x) {
+    if (lu_skip_mask() & 16) return x.err;
     // x = U^{-1} y, block rows from the bottom
     int64_t nblk = cdiv64(x.N, LU_NBO);
     bhs_prof_begin(BHS_PROF_LU_RHS, x.st);
