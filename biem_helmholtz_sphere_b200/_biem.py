@@ -494,13 +494,14 @@ def _sweep_shape(N: int, K: int) -> tuple[int, int]:
     2 x 16 -> 142, 8 x 8 -> 144, 4 x 16 -> 146, 2 x 32 -> 147: independent streams matter more than fewer launches.
     With the round-2 kernels (3M trailing update) the curve is flat at the top: 2 x 32 -> 165, 2 x 64 -> 165, 4 x 24 -> 164,
     4 x 32 -> 167 (tools/sweep_shapes.sh).  Defaults: 32 groups of 4 systems for long sweeps (128 systems in flight, 34 GB at
-    N = 4096), groups of 2 below 128 systems (more independent streams for the same number in flight); capped so that the
+    N = 4096), groups of 2 below 64 systems (more independent streams for the same number in flight; tools/sweep_short.sh: 32
+    systems 2 x 16 -> 170, 4 x 8 -> 168, 1 x 32 -> 151; 64 systems 2 x 32 -> 174, 4 x 16 -> 179); capped so that the
     buffers use at most a quarter of the free device memory.  Override with BHS_SWEEP_BATCH / BHS_SWEEP_SLOTS."""
     import os
 
     if K <= 1 or N > 12000:
         return 1, 1
-    batch = max(1, int(os.environ.get("BHS_SWEEP_BATCH", "4" if K >= 128 else "2")))
+    batch = max(1, int(os.environ.get("BHS_SWEEP_BATCH", "4" if K >= 64 else "2")))
     batch = min(batch, K)
     free, _ = torch.cuda.mem_get_info()
     fit = max(1, int(free // 4 // (16 * N * N)))  # systems that fit
