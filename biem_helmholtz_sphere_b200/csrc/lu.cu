@@ -1828,9 +1828,9 @@ static int lu_factor(LuCtx& x) {
     // Outer block width without look-ahead: 256 with the tensor-map GEMM.  The trailing update then runs 256-deep k loops (half
     // as many passes over C, a longer steady state per tile), at the price of a 128-deep update inside the block; the panel chain
     // gets longer, which only matters for a lone system (those take the look-ahead path above, 128 wide).  BHS_LU_NBO overrides.
-    static const int nbo_env = [] { const char* e = getenv("BHS_LU_NBO"); return e ? atoi(e) : 0; }();
+    const int nbo_env = [] { const char* e = getenv("BHS_LU_NBO"); return e ? atoi(e) : 0; }();  // (read per call: tests vary it)
     x.nbo = x.tma ? 256 : LU_NBO;
-    static const bool defer_off = getenv("BHS_LU_PERM_NOW") != nullptr;  // A/B: every panel interchanges all N columns at once
+    const bool defer_off = getenv("BHS_LU_PERM_NOW") != nullptr;  // A/B: every panel interchanges all N columns at once
     x.defer_perm = !gemm_only && !defer_off;
     if (nbo_env >= LU_NBO && nbo_env % LU_NBO == 0 && x.tma) x.nbo = nbo_env;
     for (int64_t J = 0; J < x.N; J += x.nbo) {
