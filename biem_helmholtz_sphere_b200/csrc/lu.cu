@@ -1669,7 +1669,8 @@ static void lu_panel(LuCtx& x, int64_t j, int w) {
         const bool local = x.lookahead || x.defer_perm;
         const int64_t c_lo = local ? x.J : 0;
         const int64_t c_hi = local ? (x.J + x.nbo < x.N ? x.J + x.nbo : x.N) : x.N;
-        const int nct = (int)cdiv64(c_hi - c_lo, PERM_COLS), nrt = x.rhs ? (int)cdiv64(x.nrhs, PERM_COLS) : 0;
+        // (with look-ahead the right-hand sides are interchanged and solved on the update stream, off the panel chain)
+        const int nct = (int)cdiv64(c_hi - c_lo, PERM_COLS), nrt = (x.rhs && !x.lookahead) ? (int)cdiv64(x.nrhs, PERM_COLS) : 0;
         lu_permute_kernel<<<dim3((unsigned)(nct + nrt), 1, x.nbatch), 256, 0, x.st>>>(
             x.A, x.ld, c_lo, c_hi - c_lo, nct, x.rhs, x.nrhs, j, 1, w, x.dblk, pmap_j, x.bs.sA, x.bs.sRhs, x.bs.sDblk, x.bs.sPmap);
         LU_LAUNCH_CHECK(x);
@@ -1727,6 +1728,20 @@ static void lu_permute_deferred(LuCtx& x, int64_t J, int w, int64_t c_lo, int64_
     LU_LAUNCH_CHECK(x);
 }
 
+// The interchanges of the panels of the outer block at J applied to the right-hand sides only (look-ahead: the panel-time
+// launches skip them).
+static void lu_permute_rhs(LuCtx& x, int64_t J, int w) {
+    if (!x.rhs || (lu_skip_mask() & 3)) return;
+    const int npan = (w + LU_NB - 1) / LU_NB, wlast = w - (npan - 1) * LU_NB;
+    const int nrt = (int)cdiv64(x.nrhs, PERM_COLS);
+    bhs_prof_begin(BHS_PROF_LU_RHS, x.st);
+    lu_permute_kernel<<<dim3((unsigned)nrt, 1, x.nbatch), 256, 0, x.st>>>(x.A, x.ld, 0, 0, 0, x.rhs, x.nrhs, J, npan, wlast, nullptr,
+                                                                          x.pmaps + (J / LU_NB) * LU_PMAP, x.bs.sA, x.bs.sRhs,
+                                                                          x.bs.sDblk, x.bs.sPmap);
+    bhs_prof_end(BHS_PROF_LU_RHS, 0.0, x.st);
+    LU_LAUNCH_CHECK(x);
+}
+
 static void lu_rhs_forward(LuCtx& x, int64_t J, int w) {
     if (lu_skip_mask() & 16) return;
     // forward substitution of this block row: y_J = L11^{-1} rhs_J ; rhs_below -= L21 y_J
@@ -1778,7 +1793,6 @@ static int lu_factor_lookahead(LuCtx& x, cudaStream_t pst) {
         x.J = J;
         x.st = pst;
         lu_rec(x, J, w);
-        if (x.rhs) lu_rhs_forward(x, J, w);
         last_J = J;
         last_w = w;
         cudaEventRecord(e_panel, pst);
@@ -1792,7 +1806,16 @@ static int lu_factor_lookahead(LuCtx& x, cudaStream_t pst) {
             lu_gemm(x, J + w, x.N, J + w, nc_hi, J, w);  // the next block column first
             cudaEventRecord(e_next, ust);
             cudaStreamWaitEvent(pst, e_next, 0);
-            lu_gemm(x, J + w, x.N, nc_hi, x.N, J, w);    // the rest overlaps the panels of the next block
+            // everything below overlaps the panels of the next block: the right-hand sides of this block row (interchanges,
+            // forward substitution) and the rest of the trailing update
+            if (x.rhs) {
+                lu_permute_rhs(x, J, w);
+                lu_rhs_forward(x, J, w);
+            }
+            lu_gemm(x, J + w, x.N, nc_hi, x.N, J, w);
+        } else if (x.rhs) {
+            lu_permute_rhs(x, J, w);
+            lu_rhs_forward(x, J, w);
         }
     }
     // the interchanges of the last block's panels on the columns left of it
