@@ -501,6 +501,21 @@ def _sweep_shape(N: int, K: int) -> tuple[int, int]:
 
     if K <= 1 or N > 12000:
         return 1, 1
+    # cudaMemGetInfo costs ~20 ms of host time with the device idle: ask once per (device, N, K, overrides)
+    key = (torch.cuda.current_device(), N, K, os.environ.get("BHS_SWEEP_BATCH"), os.environ.get("BHS_SWEEP_SLOTS"))
+    hit = _shape_cache.get(key)
+    if hit is not None:
+        return hit
+    _shape_cache[key] = shape = _sweep_shape_uncached(N, K)
+    return shape
+
+
+_shape_cache: dict = {}
+
+
+def _sweep_shape_uncached(N: int, K: int) -> tuple[int, int]:
+    import os
+
     batch = max(1, int(os.environ.get("BHS_SWEEP_BATCH", "4" if K >= 64 else "2")))
     batch = min(batch, K)
     free, _ = torch.cuda.mem_get_info()
@@ -542,6 +557,7 @@ def _uscat_streams(n: int = 8):
 def clear_engines() -> None:
     """Drop cached sweep engines (frees their N x N slot buffers)."""
     _engines.clear()
+    _shape_cache.clear()
 
 
 # --------------------------------------------------------------------------------------------------
