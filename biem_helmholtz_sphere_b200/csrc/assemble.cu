@@ -693,12 +693,12 @@ static bool asm_reg_shape(const bhs_plan* p, int B, int nsys, int* stage_bytes, 
     const int64_t sub = (int64_t)nsys * ucap * p->H2 * (int64_t)sizeof(cplx);
     if (stage_bytes) *stage_bytes = sb;
     if (su_bytes) *su_bytes = 0;
-    const bool legacy = getenv("BHS_ASM_LEGACY") != nullptr;  // A/B switch (read per call): the shared-memory-resident kernel
-    if (legacy || B < 2 || p->max_nt > 32 || (int64_t)p->max_sy_cnt * (int64_t)sizeof(cplx) > 48 * 1024 ||
-        sub > ((int64_t)1 << 30))
+    if (B < 2 || p->max_nt > 32 || (int64_t)p->max_sy_cnt * (int64_t)sizeof(cplx) > 48 * 1024 || sub > ((int64_t)1 << 30))
         return false;
+    // the workspace layout depends on the shape only -- not on the A/B switch below, which may change between the
+    // workspace query and the call (tests flip it while a caller keeps its workspace)
     if (su_bytes) *su_bytes = sub;
-    return true;
+    return getenv("BHS_ASM_LEGACY") == nullptr;  // A/B switch (read per call): set = the shared-memory-resident kernel
 }
 
 // ---- host entries -------------------------------------------------------------------------------------------
@@ -749,7 +749,8 @@ static AsmWork carve(const bhs_plan* p, int B, int nsys, void* base) {
     w.members = (int32_t*)take(np * 4);
     {
         int64_t su_bytes = 0;
-        w.Su = asm_reg_shape(p, B, nsys, nullptr, &su_bytes) ? (cplx*)take(su_bytes) : nullptr;
+        asm_reg_shape(p, B, nsys, nullptr, &su_bytes);
+        w.Su = su_bytes > 0 ? (cplx*)take(su_bytes) : nullptr;
     }
     {
         int n_store, T;
