@@ -1510,7 +1510,7 @@ static LuWork lu_carve(int64_t N, int nbatch, void* base) {
 // BHS_LU_SKIP (measurement aid, WRONG results): bit mask of kernel families that are not launched, to see what each costs a
 // sweep -- 1: pivot selection + interchanges + L21 (the whole panel), 2: interchanges only, 4: 32-row triangular solves,
 // 8: updates with K < 128, 16: right-hand-side kernels, 32: the K = 128 update inside a 256-wide block, 64: the K = 128 update
-// inside its U12 solve.
+// inside its U12 solve, 128: the trailing updates (K = outer block width).
 static int lu_skip_mask() {
     static const int m = [] { const char* e = getenv("BHS_LU_SKIP"); return e ? atoi(e) : 0; }();
     return m;
@@ -1521,6 +1521,7 @@ static void lu_pack_l(LuCtx& x, int64_t r_lo, int64_t r_hi, int64_t k0, int K);
 static void lu_gemm(LuCtx& x, int64_t r_lo, int64_t r_hi, int64_t c_lo, int64_t c_hi, int64_t k0, int K) {
     if (r_lo >= r_hi || c_lo >= c_hi || K <= 0) return;
     if ((lu_skip_mask() & 8) && K < LU_NBO) return;
+    if ((lu_skip_mask() & 128) && K > LU_NBO) return;
     const int pcat = (K >= LU_NBO || (k0 == x.J && r_lo >= x.J + LU_NBO)) ? BHS_PROF_LU_GEMM : BHS_PROF_LU_GEMM_IN;
     if (x.tma) {
         bhs_prof_begin(pcat, x.st);
