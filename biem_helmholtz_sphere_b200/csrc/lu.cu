@@ -12,7 +12,8 @@
 //   pipeline stage is two 1-D TMA bulk copies (cp.async.bulk + mbarrier), 3 stages deep.
 #include <cstdlib>
 
-#include <cuda.h>  // CUtensorMap types only; the encoder is fetched with cudaGetDriverEntryPoint
+#include <cuda.h>
+#include <type_traits>  // CUtensorMap types only; the encoder is fetched with cudaGetDriverEntryPoint
 
 #include "common.cuh"
 #include "prof.h"
@@ -1040,90 +1041,103 @@ __global__ void __launch_bounds__(CP_THREADS, 1)
     __syncthreads();
     if (csz > 1) cluster_sync_all();  // every CTA's barriers are initialised before anybody sends
     const int ncb = (w + CP_Q - 1) / CP_Q;
+    // The step loop runs in four phases of four column groups.  In the phase that starts at group 4 p only the first
+    // LIVE = CP_LC - 4 p register slots still hold unfinished columns (finished ones travel round the back of the rotation), so
+    // that phase publishes, exchanges and updates LIVE slots instead of CP_LC: no predicated-off column work, and the
+    // cluster exchange shrinks from 34 to 26 / 18 / 10 sixteen-byte chunks per peer.
+    auto phase = [&](auto live_c, int cb_begin, int cb_end) {
+        constexpr int LIVE = decltype(live_c)::value;
+        constexpr int NCH = 2 + CP_Q * LIVE;  // chunks of a slot that are sent: {key, row}, 1/pivot, the live row entries
 #pragma unroll 1
-    for (int cb = 0; cb < ncb; ++cb) {
+        for (int cb = cb_begin; cb < cb_end; ++cb) {
 #pragma unroll
-        for (int gg = 0; gg < CP_Q; ++gg) {
-            const int c = CP_Q * cb + gg;
-            if (c < w) {
-                const int buf = c & 1;
-                const double mag = fabs(x[0].x) + fabs(x[0].y);
-                const unsigned long long key =
-                    (active && g == gg) ? (unsigned long long)__double_as_longlong(mag) + 1ULL : 0ULL;
-                int bl;
-                const unsigned long long wbest = warp_argmax_u64(key, bl);
-                cplx xc;  // this row's entry in the pivot column, for both lanes of the pair
-                xc.x = __shfl_sync(0xffffffffu, x[0].x, (lane & ~(CP_Q - 1)) | gg);
-                xc.y = __shfl_sync(0xffffffffu, x[0].y, (lane & ~(CP_Q - 1)) | gg);
-                if (pair == bl / CP_Q) {
-                    if (lane == bl) {
-                        wkey[buf][warp] = wbest;
-                        wrow[buf][warp] = myrow;
-                        if (wbest) prinv[buf][warp] = wbest > 1ULL ? crecip_fast(x[0]) : cmake(0.0, 0.0);
-                    }
-                    if (wbest) {
-#pragma unroll
-                        for (int i = 0; i < CP_LC; ++i) prow[buf][warp][CP_Q * i + g] = x[i];  // rotated like x
-                    }
-                }
-                __syncthreads();
-                int bw;
-                const unsigned long long ctabest = warp_argmax_u64(wkey[buf][lane & (CP_NW - 1)], bw);
-                unsigned long long best = ctabest;
-                const cplx* pr = prow[buf][bw];
-                cplx rinv = prinv[buf][bw];
-                int32_t winrow = wrow[buf][bw];
-                if (csz > 1) {
-                    if (tid == 0) mbar_expect_tx(&cbar[buf], csz * (uint32_t)sizeof(CpSlot));
-                    const uint32_t my_slot = smem_u32(&cslot[buf][rank]), my_bar = smem_u32(&cbar[buf]);
-                    for (int t = tid; t < CP_SLOT_CHUNKS * (int)csz; t += CP_THREADS) {
-                        const uint32_t peer = t / CP_SLOT_CHUNKS, ch = t % CP_SLOT_CHUNKS;
-                        unsigned long long v0, v1;
-                        if (ch == 0) {
-                            v0 = ctabest;
-                            v1 = (unsigned long long)(uint32_t)winrow;
-                        } else {
-                            const cplx e = ch == 1 ? rinv : pr[ch - 2];
-                            v0 = (unsigned long long)__double_as_longlong(e.x);
-                            v1 = (unsigned long long)__double_as_longlong(e.y);
+            for (int gg = 0; gg < CP_Q; ++gg) {
+                const int c = CP_Q * cb + gg;
+                if (c < w) {
+                    const int buf = c & 1;
+                    const double mag = fabs(x[0].x) + fabs(x[0].y);
+                    const unsigned long long key =
+                        (active && g == gg) ? (unsigned long long)__double_as_longlong(mag) + 1ULL : 0ULL;
+                    int bl;
+                    const unsigned long long wbest = warp_argmax_u64(key, bl);
+                    cplx xc;  // this row's entry in the pivot column, for both lanes of the pair
+                    xc.x = __shfl_sync(0xffffffffu, x[0].x, (lane & ~(CP_Q - 1)) | gg);
+                    xc.y = __shfl_sync(0xffffffffu, x[0].y, (lane & ~(CP_Q - 1)) | gg);
+                    if (pair == bl / CP_Q) {
+                        if (lane == bl) {
+                            wkey[buf][warp] = wbest;
+                            wrow[buf][warp] = myrow;
+                            if (wbest) prinv[buf][warp] = wbest > 1ULL ? crecip_fast(x[0]) : cmake(0.0, 0.0);
                         }
-                        st_async_16(mapa_shared(my_slot + ch * 16, peer), v0, v1, mapa_shared(my_bar, peer));
-                    }
-                    while (!mbar_try_wait(&cbar[buf], (uint32_t)(c >> 1) & 1u)) {
-                    }
-                    int bc;
-                    best = warp_argmax_u64(lane < (int)csz ? cslot[buf][lane].key : 0ULL, bc);  // lowest rank wins a tie
-                    pr = cslot[buf][bc].prow;
-                    rinv = cslot[buf][bc].rinv;
-                    winrow = cslot[buf][bc].row;
-                }
-                const bool any = best != 0ULL;     // at least one active row left
-                const bool nonzero = best > 1ULL;  // its pivot entry is not exactly zero
-                if (tid == 0) {
-                    s_win[c] = any ? winrow : -1;
-                    if (rank == 0 && any && !nonzero) atomicCAS(fin.info, 0, (int)(fin.j + c + 1));
-                }
-                if (any && active && myrow == winrow) {  // the pivot row IS row c of the factored diagonal block
+                        if (wbest) {
 #pragma unroll
-                    for (int i = 0; i < CP_LC; ++i) fin.dblk[c * LU_NB + CP_Q * ((cb + i) & (CP_LC - 1)) + g] = x[i];
-                    active = false;
-                }
-                if (any && active && nonzero) {
-                    const cplx l = cmul(xc, rinv);
-                    const cplx ml = cmake(-l.x, -l.y);
-                    if (g == gg) x[0] = l;
-                    else if (g > gg) x[0] = cfma(ml, pr[g], x[0]);
+                            for (int i = 0; i < LIVE; ++i) prow[buf][warp][CP_Q * i + g] = x[i];  // rotated like x
+                        }
+                    }
+                    __syncthreads();
+                    int bw;
+                    const unsigned long long ctabest = warp_argmax_u64(wkey[buf][lane & (CP_NW - 1)], bw);
+                    unsigned long long best = ctabest;
+                    const cplx* pr = prow[buf][bw];
+                    cplx rinv = prinv[buf][bw];
+                    int32_t winrow = wrow[buf][bw];
+                    if (csz > 1) {
+                        if (tid == 0) mbar_expect_tx(&cbar[buf], csz * (uint32_t)(NCH * 16));
+                        const uint32_t my_slot = smem_u32(&cslot[buf][rank]), my_bar = smem_u32(&cbar[buf]);
+                        for (int t = tid; t < NCH * (int)csz; t += CP_THREADS) {
+                            const uint32_t peer = t / NCH, ch = t % NCH;
+                            unsigned long long v0, v1;
+                            if (ch == 0) {
+                                v0 = ctabest;
+                                v1 = (unsigned long long)(uint32_t)winrow;
+                            } else {
+                                const cplx e = ch == 1 ? rinv : pr[ch - 2];
+                                v0 = (unsigned long long)__double_as_longlong(e.x);
+                                v1 = (unsigned long long)__double_as_longlong(e.y);
+                            }
+                            st_async_16(mapa_shared(my_slot + ch * 16, peer), v0, v1, mapa_shared(my_bar, peer));
+                        }
+                        while (!mbar_try_wait(&cbar[buf], (uint32_t)(c >> 1) & 1u)) {
+                        }
+                        int bc;
+                        best = warp_argmax_u64(lane < (int)csz ? cslot[buf][lane].key : 0ULL, bc);  // lowest rank wins a tie
+                        pr = cslot[buf][bc].prow;
+                        rinv = cslot[buf][bc].rinv;
+                        winrow = cslot[buf][bc].row;
+                    }
+                    const bool any = best != 0ULL;     // at least one active row left
+                    const bool nonzero = best > 1ULL;  // its pivot entry is not exactly zero
+                    if (tid == 0) {
+                        s_win[c] = any ? winrow : -1;
+                        if (rank == 0 && any && !nonzero) atomicCAS(fin.info, 0, (int)(fin.j + c + 1));
+                    }
+                    if (any && active && myrow == winrow) {  // the pivot row IS row c of the factored diagonal block
 #pragma unroll
-                    for (int i = 1; i < CP_LC; ++i)
-                        if (cb + i < CP_LC) x[i] = cfma(ml, pr[CP_Q * i + g], x[i]);
+                        for (int i = 0; i < CP_LC; ++i) fin.dblk[c * LU_NB + CP_Q * ((cb + i) & (CP_LC - 1)) + g] = x[i];
+                        active = false;
+                    }
+                    if (any && active && nonzero) {
+                        const cplx l = cmul(xc, rinv);
+                        const cplx ml = cmake(-l.x, -l.y);
+                        if (g == gg) x[0] = l;
+                        else if (g > gg) x[0] = cfma(ml, pr[g], x[0]);
+#pragma unroll
+                        for (int i = 1; i < LIVE; ++i)
+                            if (cb + i < CP_LC) x[i] = cfma(ml, pr[CP_Q * i + g], x[i]);
+                    }
                 }
             }
-        }
-        const cplx t = x[0];
+            const cplx t = x[0];
 #pragma unroll
-        for (int i = 1; i < CP_LC; ++i) x[i - 1] = x[i];
-        x[CP_LC - 1] = t;
-    }
+            for (int i = 1; i < CP_LC; ++i) x[i - 1] = x[i];
+            x[CP_LC - 1] = t;
+        }
+    };
+    static_assert(CP_LC == 16, "the four phases below assume 16 register slots per lane");
+    phase(std::integral_constant<int, 16>{}, 0, ncb < 4 ? ncb : 4);
+    phase(std::integral_constant<int, 12>{}, 4, ncb < 8 ? ncb : 8);
+    phase(std::integral_constant<int, 8>{}, 8, ncb < 12 ? ncb : 12);
+    phase(std::integral_constant<int, 4>{}, 12, ncb);
     // rows that never pivoted hold their multipliers: that is L21 (only when every row of the panel was a candidate)
     if (write_l21 && active) {
         cplx* dst = A + (int64_t)myrow * ld + col0;
