@@ -37,3 +37,21 @@ def test_translation_addition_theorem(btype, n_end, k):
         lhs = S[deg < nlow]
         rhs = (T @ R)[deg < nlow]
         assert np.max(np.abs(lhs - rhs)) < 1e-9 * np.max(np.abs(lhs)), (btype, np.max(np.abs(lhs - rhs)))
+
+
+@pytest.mark.parametrize("btype,n_end,k", [("a", 12, 1.7), ("ba", 9, 0.9), ("ba", 9, 1.4 + 0.3j), ("bba", 6, 1.1), ("bbba", 4, 1.2)])
+def test_translation_block_sign_symmetry(btype, n_end, k):
+    """(S|R)_{h',h}(-t) = (-1)^(n + n') (S|R)_{h',h}(t): every term of an entry has n'' = n + n' (mod 2) and
+    S_{h''}(-t) = (-1)^{n''} S_{h''}(t).  The assembly kernel relies on it: the block of the ball pair (b', b) is derived from
+    the block of (b, b') by that sign pattern (csrc/assemble.cu, pair_rep_kernel / assemble_reg_kernel), for any geometry."""
+    d = len(btype) + 1
+    rng = np.random.default_rng(11)
+    deg = bo.degree_table(btype, n_end)
+    sign = np.where((deg[:, None] + deg[None, :]) % 2 == 0, 1.0, -1.0)
+    for _ in range(3):
+        t = rng.normal(size=d)
+        t *= rng.uniform(2.5, 6.0) / np.linalg.norm(t)
+        Tp = bo.translation_coef(btype, t[:, None], k, n_end)[0]
+        Tm = bo.translation_coef(btype, -t[:, None], k, n_end)[0]
+        scale = np.max(np.abs(Tp))
+        assert np.max(np.abs(Tm - sign * Tp)) < 1e-12 * scale
