@@ -955,6 +955,7 @@ __global__ void __launch_bounds__(LU_R) lu_select_unrolled_kernel(const cplx* __
 #define CP_NW (CP_THREADS / 32)
 #define CP_LC (LU_NB / CP_Q)
 #define CP_MAXC 16
+#define CP_PERM_COLS 64  // columns per tile of the fused row interchange (as lu_permute_kernel)
 #define CP_SLOT_CHUNKS (2 + LU_NB)  // 16-byte chunks of a slot: {key, row}, 1/pivot, 32 row entries
 struct __align__(16) CpSlot {
     unsigned long long key;
@@ -999,18 +1000,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 
 __global__ void __launch_bounds__(CP_THREADS, 1)
     lu_panel_cluster_kernel(cplx* __restrict__ A, int64_t ld, int64_t col0, int w, const int32_t* __restrict__ rows_in, int64_t n_in,
-                            int64_t row_begin, int64_t row_end, SelectFinal fin, int write_l21, LuBatch bs) {
+                            int64_t row_begin, int64_t row_end, SelectFinal fin, int write_l21, LuBatch bs, int64_t perm_c_lo,
+                            int64_t perm_c_hi) {
     A += (int64_t)blockIdx.z * bs.sA;
     if (rows_in) rows_in += (int64_t)blockIdx.z * bs.sCand;
     fin.ipiv += (int64_t)blockIdx.z * bs.sIpiv;
     fin.info += blockIdx.z;
     fin.dblk += (int64_t)blockIdx.z * bs.sDblk;
     fin.pmap += (int64_t)blockIdx.z * bs.sPmap;
-    __shared__ cplx prow[2][CP_NW][LU_NB];
+    // the published pivot rows and the exchange slots share one buffer with the row tile of the fused interchange (below)
+    constexpr size_t CP_PROW_BYTES = sizeof(cplx) * 2 * CP_NW * LU_NB, CP_SLOT_BYTES = sizeof(CpSlot) * 2 * CP_MAXC;
+    static_assert(CP_PROW_BYTES + CP_SLOT_BYTES >= sizeof(cplx) * LU_NB * CP_PERM_COLS, "row tile of the fused interchange");
+    __shared__ __align__(16) unsigned char s_raw[CP_PROW_BYTES + CP_SLOT_BYTES];
+    cplx(*prow)[CP_NW][LU_NB] = reinterpret_cast<cplx(*)[CP_NW][LU_NB]>(s_raw);
+    CpSlot(*cslot)[CP_MAXC] = reinterpret_cast<CpSlot(*)[CP_MAXC]>(s_raw + CP_PROW_BYTES);
     __shared__ cplx prinv[2][CP_NW];
     __shared__ unsigned long long wkey[2][CP_NW];
     __shared__ int32_t wrow[2][CP_NW];
-    __shared__ CpSlot cslot[2][CP_MAXC];
     __shared__ __align__(8) uint64_t cbar[2];
     __shared__ int32_t s_win[LU_NB];
     const uint32_t rank = cluster_ctarank(), csz = cluster_nctarank();
@@ -1151,6 +1157,58 @@ __global__ void __launch_bounds__(CP_THREADS, 1)
     if (rank == 0) {
         __syncthreads();
         select_finish(fin, w, s_win, tid);
+    }
+    // Fused row interchange (look-ahead path: the columns [perm_c_lo, perm_c_hi) of the current outer block): what
+    // lu_permute_kernel would do in a launch of its own right after this one.  The panel's net row map (rank 0, select_finish)
+    // and every CTA's L21 / diagonal-block stores are made visible by one more cluster barrier; CTA r then moves the rows of the
+    // column tiles r, r + csz, ...  All global loads of a tile are independent (the 32 rows of the diagonal block go through
+    // shared memory).
+    if (perm_c_hi > perm_c_lo) {
+        __threadfence();
+        if (csz > 1) cluster_sync_all();
+        else __syncthreads();
+        cplx(*tile)[CP_PERM_COLS] = reinterpret_cast<cplx(*)[CP_PERM_COLS]>(s_raw);
+        __shared__ int32_t s_map[2 * LU_NB];
+        const int ntile = (int)((perm_c_hi - perm_c_lo + CP_PERM_COLS - 1) / CP_PERM_COLS);
+        const int64_t j = fin.j;
+        const int col = tid & (CP_PERM_COLS - 1), q0 = (tid / CP_PERM_COLS) * (LU_NB / (CP_THREADS / CP_PERM_COLS));
+        constexpr int RPT = LU_NB / (CP_THREADS / CP_PERM_COLS);  // rows per thread: 512 threads = 64 columns x 8 row groups
+        for (int tl = (int)rank; tl < ntile; tl += (int)csz) {
+            const int64_t c = perm_c_lo + (int64_t)tl * CP_PERM_COLS + col;
+            const bool valid = c < perm_c_hi;
+            __syncthreads();  // the previous tile (or the exchange buffers) are no longer read
+            if (tid < 2 * LU_NB) s_map[tid] = __ldcg(fin.pmap + tid);
+            if (valid) {
+#pragma unroll
+                for (int i = 0; i < RPT; ++i)
+                    if (q0 + i < w) tile[q0 + i][col] = __ldcg(A + (j + q0 + i) * ld + c);
+            }
+            __syncthreads();
+            cplx v[RPT];
+            if (valid) {
+#pragma unroll
+                for (int i = 0; i < RPT; ++i) {
+                    const int q = q0 + i;
+                    if (q < w) {
+                        const int64_t src = s_map[q];
+                        v[i] = (src < j + w) ? tile[src - j][col] : __ldcg(A + src * ld + c);
+                    }
+                }
+            }
+            __syncthreads();  // the rows read above are overwritten below, possibly by another thread of the column
+            if (valid) {
+                const bool in_panel = c >= j && c < j + w;
+#pragma unroll
+                for (int i = 0; i < RPT; ++i) {
+                    const int q = q0 + i;
+                    if (q < w) {
+                        A[(j + q) * ld + c] = in_panel ? __ldcg(fin.dblk + q * LU_NB + (c - j)) : v[i];
+                        const int64_t dst = s_map[LU_NB + q];
+                        if (dst >= 0) A[dst * ld + c] = tile[q][col];
+                    }
+                }
+            }
+        }
     }
 }
 
@@ -1632,7 +1690,7 @@ static void lu_panel(LuCtx& x, int64_t j, int w) {
         LU_LAUNCH_CHECK(x);
     };
     cluster_init();
-    bool l21_done = false, done = false;
+    bool l21_done = false, done = false, perm_fused = false;
     const bool use_cluster = g_cluster_mode && (x.nbatch == 1 || g_cluster_mode >= 2) && M > LU_R;
     if (use_cluster) {
         // tournament rounds until one cluster can hold the candidates, then partial pivoting inside the cluster
@@ -1656,10 +1714,20 @@ static void lu_panel(LuCtx& x, int64_t j, int w) {
         at[0].val.clusterDim.x = csz; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         const int direct = rows_in == nullptr;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, lu_panel_cluster_kernel, x.A, x.ld, j, w, rows_in, n_in, j, x.N, fin, direct, x.bs);
+        // with look-ahead the interchange of the block's own columns is fused into the panel kernel (one launch less per panel
+        // on the chain that bounds a lone system; BHS_LU_FUSE_PERM=0 keeps the separate launch)
+        static const bool fuse_off = [] { const char* e = getenv("BHS_LU_FUSE_PERM"); return e && atoi(e) == 0; }();
+        int64_t pc_lo = 0, pc_hi = 0;
+        if (x.lookahead && !fuse_off && !(lu_skip_mask() & 2)) {
+            pc_lo = x.J;
+            pc_hi = x.J + x.nbo < x.N ? x.J + x.nbo : x.N;
+        }
+        cudaError_t e = cudaLaunchKernelEx(&cfg, lu_panel_cluster_kernel, x.A, x.ld, j, w, rows_in, n_in, j, x.N, fin, direct, x.bs,
+                                           pc_lo, pc_hi);
         if (e == cudaSuccess) {
             BHS_COUNT_LAUNCH();
             done = true;
+            perm_fused = pc_hi > pc_lo;
             l21_done = direct;
         } else {
             cudaGetLastError();   // this device cannot place the cluster after all: tournament from here on
@@ -1678,7 +1746,7 @@ static void lu_panel(LuCtx& x, int64_t j, int w) {
             nsets = nsets2;
         }
     }
-    if (!(lu_skip_mask() & 2)) {
+    if (!(lu_skip_mask() & 2) && !perm_fused) {
         // row interchanges: every column (and the right-hand sides) now -- or, with look-ahead, only the columns of the outer
         // block being factorised; the columns left and right of it follow on the side stream (lu_permute_deferred)
         const bool local = x.lookahead || x.defer_perm;
