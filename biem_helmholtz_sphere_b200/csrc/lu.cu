@@ -1882,15 +1882,15 @@ static int lu_factor_lookahead(LuCtx& x, cudaStream_t pst) {
         x.st = ust;
         cudaStreamWaitEvent(ust, e_panel, 0);  // (after the last block this is the join)
         if (J + w < x.N) {
-            lu_permute_deferred(x, J, w, 0, J);
             lu_permute_deferred(x, J, w, J + w, x.N);
             lu_trsm(x, J, w, J + w, x.N);
             const int64_t nc_hi = (J + w + LU_NBO < x.N) ? J + w + LU_NBO : x.N;
             lu_gemm(x, J + w, x.N, J + w, nc_hi, J, w);  // the next block column first
             cudaEventRecord(e_next, ust);
             cudaStreamWaitEvent(pst, e_next, 0);
-            // everything below overlaps the panels of the next block: the right-hand sides of this block row (interchanges,
-            // forward substitution) and the rest of the trailing update
+            // everything below overlaps the panels of the next block: the interchanges on the columns LEFT of this block, the
+            // right-hand sides of this block row (interchanges, forward substitution) and the rest of the trailing update
+            lu_permute_deferred(x, J, w, 0, J);
             if (x.rhs) {
                 lu_permute_rhs(x, J, w);
                 lu_rhs_forward(x, J, w);
