@@ -1691,7 +1691,12 @@ static void lu_panel(LuCtx& x, int64_t j, int w) {
     };
     cluster_init();
     bool l21_done = false, done = false, perm_fused = false;
-    const bool use_cluster = g_cluster_mode && (x.nbatch == 1 || g_cluster_mode >= 2) && M > LU_R;
+    // Small groups (the sweep engine forms groups of 2 for short sweeps, e.g. one rank's share at 8 GPUs) also take the cluster
+    // panel once at most 1024 rows are left: in a short sweep every group reaches its latency-bound last panels at the same
+    // time, with nothing left to overlap them, and the one-launch panel shortens exactly that tail (BHS_LU_TAIL=0: off).
+    static const int tail_rows = [] { const char* e = getenv("BHS_LU_TAIL"); return e ? atoi(e) : 1024; }();
+    const bool tail = x.nbatch <= 2 && M <= tail_rows;
+    const bool use_cluster = g_cluster_mode && (x.nbatch == 1 || g_cluster_mode >= 2 || tail) && M > LU_R;
     if (use_cluster) {
         // tournament rounds until one cluster can hold the candidates, then partial pivoting inside the cluster
         const int64_t cap = (int64_t)g_cluster_max * CP_ROWS;
